@@ -1,0 +1,699 @@
+// rm2_engine.cu -- host side of libfilmyou_rm2.so: context, C ABI (include/filmyou_rm2.h) and the
+// stream-ordered pipeline that replaces jobs RM2-1..3 of M/rm/RM2Job.java:76-100.
+//
+// Pipeline of fy_rm2_run (everything on one CUDA stream, two host sync points for sizes):
+//   index : ratings -> (user rank, item) sort -> CSR; (item, user rank) sort -> CSC; user sums,
+//           truncated total, p(i|C); per-cluster local item numbering; d, alpha, c(u,j)
+//   per cluster of this shard:  k_build_H  ->  k_score<L>  ->  k_topn
+//   pack  : dense [user x N] results -> packed triples
+// cub::DeviceRadixSort / DeviceScan are used for the two plumbing sorts and two scans only; every
+// kernel on the scoring path is in rm2_kernels.cuh.
+#include "../../include/filmyou_rm2.h"
+#include "rm2_kernels.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <numeric>
+#include <vector>
+
+namespace {
+
+struct CudaFail { cudaError_t err; const char* what; int line; };
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw CudaFail{e_, #call, __LINE__}; } while (0)
+struct StatusFail { int code; };
+
+template <class T>
+struct DBuf {                      // grow-only device buffer
+    T* p = nullptr;
+    size_t cap = 0;
+    void need(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; throw CudaFail{e, "cudaMalloc", __LINE__}; }
+        cap = n;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    ~DBuf() { release(); }
+};
+
+inline int bits_for(uint64_t n_values) {   // bits needed to represent 0..n_values-1
+    int b = 1;
+    while (b < 63 && (1ull << b) < n_values) b++;
+    return b;
+}
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace
+
+struct fy_rm2_ctx {
+    fy_rm2_params prm{};
+    char err[512] = {0};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t launches = 0;
+
+    // ---- inputs ----
+    int64_t nnz = 0;
+    int32_t max_item = -1;
+    DBuf<int32_t> in_user, in_item;
+    DBuf<float> in_score;
+    bool have_ratings = false, have_clustering = false, have_results = false;
+
+    // clustering (host)
+    int32_t n_users = 0, n_clusters = 0;
+    std::vector<int32_t> h_rank_userid, h_rank_cluster, h_cstart, h_input_rank;  // input order -> rank
+    DBuf<int32_t> uid_sorted, uid_rank, rank_userid, rank_cluster, cstart;
+
+    // fine-seam overrides (rank order / item id order), empty when unused
+    DBuf<double> ext_usum, ext_iprob;
+    bool use_ext = false;
+    int32_t split = 0, n_splits = 1;
+
+    // ---- index ----
+    DBuf<uint64_t> keys_a, keys_b, keys_c;
+    DBuf<float> s_score;
+    DBuf<int32_t> src_a, csc_src, rowptr;
+    DBuf<unsigned char> cub_tmp;
+    DBuf<double> usum, isum, iprob, bvec, total, work, work_scan;
+    DBuf<unsigned long long> counters;   // [0] n_valid, [1] truncated counter, [2] bits of the smallest positive b_i
+    DBuf<int> flags, imax;
+    DBuf<int32_t> ifirst, ilast, tstart, tend, tloc, icount, item_off;
+    DBuf<int32_t> c_item, c_start, c_len, csr_loc, csc_lu, chunk_ptr;
+    DBuf<double> c_b, c_alpha, csr_delta, csc_delta, csr_c;
+    int32_t m = 0;
+    std::vector<int32_t> h_icount, h_item_off;
+    double h_total = 0.0;
+
+    // ---- per cluster ----
+    DBuf<double> H, scores;
+
+    // ---- results ----
+    int32_t shard_begin = 0, shard_end = 0, out_stride = 0;
+    DBuf<int32_t> out_item, out_count;
+    DBuf<double> out_score;
+    DBuf<int64_t> out_off, out_cnt64;
+    int64_t n_results = 0, users_scored = 0;
+    DBuf<int32_t> p_user, p_item, p_cluster;
+    DBuf<double> p_s64;
+    DBuf<float> p_s32;
+
+    // ---- co-occurrence (config 3) ----
+    DBuf<int32_t> cooc_counts;
+    int32_t cooc_items = 0;
+
+    fy_rm2_profile prof{};
+    std::vector<cudaEvent_t> events;
+
+    int fail(int code, const char* fmt, ...) {
+        va_list ap; va_start(ap, fmt); vsnprintf(err, sizeof(err), fmt, ap); va_end(ap);
+        return code;
+    }
+    cudaEvent_t ev(size_t i) {
+        while (events.size() <= i) { cudaEvent_t e; CK(cudaEventCreate(&e)); events.push_back(e); }
+        return events[i];
+    }
+};
+
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
+    do {                                                                              \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);              \
+        (ctx)->launches++;                                                            \
+        CK(cudaGetLastError());                                                       \
+    } while (0)
+
+// runs f, turning C++/CUDA failures into fy_status codes: nothing crosses the C boundary
+template <class F>
+static int guarded(fy_rm2_ctx* ctx, F&& f) {
+    try {
+        return f();
+    } catch (const CudaFail& c) {
+        const int code = (c.err == cudaErrorMemoryAllocation) ? FY_E_NOMEM : FY_E_CUDA;
+        return ctx->fail(code, "CUDA error %d (%s) at %s, rm2_engine.cu:%d", (int)c.err, cudaGetErrorString(c.err), c.what, c.line);
+    } catch (const StatusFail& s) {
+        return s.code;
+    } catch (const std::bad_alloc&) {
+        return ctx->fail(FY_E_NOMEM, "host allocation failed");
+    } catch (...) {
+        return ctx->fail(FY_E_CUDA, "unexpected exception");
+    }
+}
+
+extern "C" int fy_rm2_abi_version(void) { return FY_RM2_ABI_VERSION; }
+
+extern "C" void fy_rm2_default_params(fy_rm2_params* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->lambda = 0.1;                 // RMRecommenderDriver.java:114
+    p->number_of_items = 0;          // required (:91)
+    p->top_n = 1000;                 // :95
+    p->filter_users = 0;             // :119
+    p->device = 0;
+    p->shard_rank = 0;
+    p->shard_count = 1;
+    p->tie_break = 0;
+}
+
+extern "C" int fy_rm2_create(fy_rm2_ctx** out, const fy_rm2_params* p) {
+    if (!out || !p) return FY_E_ARG;
+    *out = nullptr;
+    if (p->top_n < 0 || p->number_of_items <= 0 || p->tie_break != 0 || !(p->lambda >= 0.0 && p->lambda <= 1.0))
+        return FY_E_ARG;
+    if (p->shard_count < 0 || (p->shard_count > 1 && (p->shard_rank < 0 || p->shard_rank >= p->shard_count)))
+        return FY_E_ARG;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || p->device < 0 || p->device >= n_dev)
+        return FY_E_CUDA;            // no CPU fallback: fail loudly
+    fy_rm2_ctx* ctx = new (std::nothrow) fy_rm2_ctx();
+    if (!ctx) return FY_E_NOMEM;
+    ctx->prm = *p;
+    if (ctx->prm.shard_count <= 0) { ctx->prm.shard_count = 1; ctx->prm.shard_rank = 0; }
+    int rc = guarded(ctx, [&]() {
+        CK(cudaSetDevice(p->device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, p->device));
+        if (prop.major < 10) return ctx->fail(FY_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", p->device, prop.major, prop.minor);
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+        return (int)FY_OK;
+    });
+    if (rc != FY_OK) { fy_rm2_destroy(ctx); return rc; }
+    *out = ctx;
+    return FY_OK;
+}
+
+extern "C" void fy_rm2_destroy(fy_rm2_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->prm.device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* fy_rm2_last_error(const fy_rm2_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+extern "C" int fy_rm2_set_stream(fy_rm2_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return FY_E_ARG;
+    return guarded(ctx, [&]() {
+        CK(cudaSetDevice(ctx->prm.device));
+        if (ctx->stream) CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->own_stream && ctx->stream) CK(cudaStreamDestroy(ctx->stream));
+        ctx->stream = (cudaStream_t)cuda_stream;
+        ctx->own_stream = false;
+        return (int)FY_OK;
+    });
+}
+
+static int check_flags(fy_rm2_ctx* ctx, const int* f) {
+    if (f[fy::DF_BAD_ITEM]) return ctx->fail(FY_E_ARG, "negative or out-of-range item id in the ratings");
+    if (f[fy::DF_UNKNOWN_USER]) return ctx->fail(FY_E_UNKNOWN_USER, "a positive rating belongs to a user absent from `clustering`");
+    if (f[fy::DF_DUPLICATE]) return ctx->fail(FY_E_DUPLICATE_RATING, "the same (user,item) pair is rated twice");
+    if (f[fy::DF_USER_WITHOUT_RATING]) return ctx->fail(FY_E_USER_WITHOUT_RATING, "`clustering` lists a user without any positive rating (AbstractRM2Reducer.java:153-160 would mis-parse the group)");
+    return FY_OK;
+}
+
+static int upload_ratings(fy_rm2_ctx* ctx, const int32_t* user, const int32_t* item, const float* score, int64_t nnz) {
+    if (nnz > 0x7fffffffll - 1024) return ctx->fail(FY_E_UNSUPPORTED, "more than 2^31 ratings");
+    CK(cudaSetDevice(ctx->prm.device));
+    ctx->have_ratings = false;
+    ctx->have_results = false;
+    ctx->in_user.need((size_t)nnz); ctx->in_item.need((size_t)nnz); ctx->in_score.need((size_t)nnz);
+    ctx->flags.need(fy::DF_COUNT); ctx->imax.need(1);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->in_user.p, user, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->in_item.p, item, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->in_score.p, score, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->flags.p, 0, sizeof(int) * fy::DF_COUNT, st));
+    CK(cudaMemsetAsync(ctx->imax.p, 0xff, sizeof(int), st));
+    if (nnz > 0) LAUNCH(ctx, fy::k_scan_ratings, cdiv(nnz, 256), 256, 0, ctx->in_item.p, ctx->in_score.p, nnz, ctx->imax.p, ctx->flags.p);
+    int h_flags[fy::DF_COUNT]; int h_max = -1;
+    CK(cudaMemcpyAsync(h_flags, ctx->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h_max, ctx->imax.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int rc = check_flags(ctx, h_flags);
+    if (rc != FY_OK) return rc;
+    if (h_max < 0) return ctx->fail(FY_E_ARG, "no rating with score > 0");
+    ctx->nnz = nnz;
+    ctx->max_item = h_max;
+    ctx->have_ratings = true;
+    return FY_OK;
+}
+
+extern "C" int fy_rm2_set_ratings(fy_rm2_ctx* ctx, const int32_t* user, const int32_t* item, const float* score, int64_t nnz) {
+    if (!ctx) return FY_E_ARG;
+    if (!user || !item || !score || nnz <= 0) return ctx->fail(FY_E_ARG, "fy_rm2_set_ratings: null pointer or nnz <= 0");
+    return guarded(ctx, [&]() { ctx->use_ext = false; return upload_ratings(ctx, user, item, score, nnz); });
+}
+
+static int upload_clustering(fy_rm2_ctx* ctx, const int32_t* user, const int32_t* cluster, int64_t n_users,
+                             const int32_t* cluster_size, int32_t n_clusters, bool check_sizes) {
+    if (n_users > 0x7ffffff0ll) return ctx->fail(FY_E_UNSUPPORTED, "too many users");
+    ctx->have_clustering = false;
+    ctx->have_results = false;
+    const int32_t U = (int32_t)n_users;
+    std::vector<int32_t> cnt((size_t)n_clusters, 0);
+    for (int32_t k = 0; k < U; k++) {
+        if (cluster[k] < 0 || cluster[k] >= n_clusters) return ctx->fail(FY_E_ARG, "cluster id %d of user %d outside [0,%d)", cluster[k], user[k], n_clusters);
+        cnt[cluster[k]]++;
+    }
+    if (check_sizes)
+        for (int32_t c = 0; c < n_clusters; c++)
+            if (cnt[c] != cluster_size[c])
+                return ctx->fail(FY_E_CLUSTER_SIZE, "clusteringCount[%d] = %d but %d users map to it", c, cluster_size[c], cnt[c]);
+    // users[] of the reducer, canonicalised: (cluster, user id) ascending
+    std::vector<int32_t> order((size_t)U);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        if (cluster[a] != cluster[b]) return cluster[a] < cluster[b];
+        return user[a] < user[b];
+    });
+    ctx->h_rank_userid.resize(U); ctx->h_rank_cluster.resize(U); ctx->h_input_rank.resize(U);
+    for (int32_t r = 0; r < U; r++) {
+        ctx->h_rank_userid[r] = user[order[r]];
+        ctx->h_rank_cluster[r] = cluster[order[r]];
+        ctx->h_input_rank[order[r]] = r;
+    }
+    ctx->h_cstart.assign((size_t)n_clusters + 1, 0);
+    for (int32_t c = 0; c < n_clusters; c++) ctx->h_cstart[c + 1] = ctx->h_cstart[c] + cnt[c];
+    // id -> rank lookup table sorted by id
+    std::vector<int32_t> by_id((size_t)U);
+    std::iota(by_id.begin(), by_id.end(), 0);
+    std::sort(by_id.begin(), by_id.end(), [&](int32_t a, int32_t b) { return ctx->h_rank_userid[a] < ctx->h_rank_userid[b]; });
+    std::vector<int32_t> ids((size_t)U), ranks((size_t)U);
+    for (int32_t k = 0; k < U; k++) { ids[k] = ctx->h_rank_userid[by_id[k]]; ranks[k] = by_id[k]; }
+    for (int32_t k = 1; k < U; k++)
+        if (ids[k] == ids[k - 1]) return ctx->fail(FY_E_ARG, "user %d appears twice in `clustering`", ids[k]);
+    CK(cudaSetDevice(ctx->prm.device));
+    ctx->uid_sorted.need(U); ctx->uid_rank.need(U); ctx->rank_userid.need(U); ctx->rank_cluster.need(U);
+    ctx->cstart.need((size_t)n_clusters + 1);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->uid_sorted.p, ids.data(), (size_t)U * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->uid_rank.p, ranks.data(), (size_t)U * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->rank_userid.p, ctx->h_rank_userid.data(), (size_t)U * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->rank_cluster.p, ctx->h_rank_cluster.data(), (size_t)U * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->cstart.p, ctx->h_cstart.data(), ((size_t)n_clusters + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // the staging vectors die at return
+    ctx->n_users = U;
+    ctx->n_clusters = n_clusters;
+    ctx->have_clustering = true;
+    return FY_OK;
+}
+
+extern "C" int fy_rm2_set_clustering(fy_rm2_ctx* ctx, const int32_t* user, const int32_t* cluster, int64_t n_users,
+                                     const int32_t* cluster_size, int32_t n_clusters) {
+    if (!ctx) return FY_E_ARG;
+    if (!user || !cluster || !cluster_size || n_users <= 0 || n_clusters <= 0)
+        return ctx->fail(FY_E_ARG, "fy_rm2_set_clustering: null pointer or empty input");
+    return guarded(ctx, [&]() { ctx->use_ext = false; ctx->n_splits = 1; ctx->split = 0;
+                                return upload_clustering(ctx, user, cluster, n_users, cluster_size, n_clusters, true); });
+}
+
+// ---------------------------------------------------------------------------------------------
+// the pipeline
+// ---------------------------------------------------------------------------------------------
+template <int L>
+static void launch_score(fy_rm2_ctx* ctx, dim3 grid, const double* H, int32_t I_c, int32_t ld, int32_t rank_begin,
+                         int32_t slot0, double log_items, double log_K) {
+    LAUNCH(ctx, fy::k_score<L>, grid, fy::SCORE_THREADS, 0, H, I_c, ld, rank_begin, slot0, ctx->rowptr.p,
+           ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, log_items, log_K, ctx->scores.p);
+}
+
+static int run_pipeline(fy_rm2_ctx* ctx) {
+    using namespace fy;
+    if (!ctx->have_ratings || !ctx->have_clustering) return ctx->fail(FY_E_STATE, "fy_rm2_run needs fy_rm2_set_ratings and fy_rm2_set_clustering first");
+    CK(cudaSetDevice(ctx->prm.device));
+    cudaStream_t st = ctx->stream;
+    ctx->have_results = false;
+    ctx->launches = 0;
+    ctx->prof = fy_rm2_profile{};
+    const int64_t nnz = ctx->nnz;
+    const int32_t U = ctx->n_users, KC = ctx->n_clusters;
+    const int32_t TI = ctx->max_item + 1;                    // direct item tables
+    if ((int64_t)KC * TI > (1ll << 28)) return ctx->fail(FY_E_UNSUPPORTED, "n_clusters * (max_item+1) = %lld exceeds the direct-table limit 2^28", (long long)KC * TI);
+    const int item_bits = bits_for((uint64_t)TI), rank_bits = bits_for((uint64_t)U);
+    const int key_bits = std::min(64, item_bits + rank_bits + 1);
+    const double lambda = ctx->prm.lambda;
+    size_t evi = 0;
+    cudaEvent_t ev_start = ctx->ev(evi++), ev_index = ctx->ev(evi++), ev_end = ctx->ev(evi++);
+    CK(cudaEventRecord(ev_start, st));
+
+    // ---------------- index: sort #1 (user rank, item) -> CSR ----------------
+    ctx->keys_a.need((size_t)nnz); ctx->keys_b.need((size_t)nnz); ctx->s_score.need((size_t)nnz);
+    ctx->counters.need(3); ctx->flags.need(DF_COUNT);
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 2 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctx->counters.p + 2, 0xff, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctx->flags.p, 0, sizeof(int) * DF_COUNT, st));
+    LAUNCH(ctx, k_make_keys, cdiv(nnz, 256), 256, 0, ctx->in_user.p, ctx->in_item.p, ctx->in_score.p, nnz,
+           ctx->uid_sorted.p, ctx->uid_rank.p, U, item_bits, ctx->max_item, ctx->keys_a.p, ctx->counters.p, ctx->flags.p);
+    {
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->keys_a.p, ctx->keys_b.p, ctx->in_score.p, ctx->s_score.p,
+                                           (int64_t)nnz, 0, key_bits, st));
+        ctx->cub_tmp.need(tmp);
+        CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, ctx->keys_a.p, ctx->keys_b.p, ctx->in_score.p, ctx->s_score.p,
+                                           (int64_t)nnz, 0, key_bits, st));
+    }
+    // sync A: number of positive ratings, input errors
+    unsigned long long h_counters[2]; int h_flags[DF_COUNT];
+    CK(cudaMemcpyAsync(h_counters, ctx->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_flags, ctx->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    { int rc = check_flags(ctx, h_flags); if (rc != FY_OK) return rc; }
+    const int32_t m = (int32_t)h_counters[0];
+    ctx->m = m;
+    if (m <= 0) return ctx->fail(FY_E_ARG, "no positive rating");
+    const uint64_t* keys = ctx->keys_b.p;                    // sorted (rank, item)
+
+    ctx->rowptr.need((size_t)U + 1);
+    ctx->usum.need(U);
+    LAUNCH(ctx, k_rows, cdiv(m, 256), 256, 0, keys, m, item_bits, U, ctx->rowptr.p, ctx->flags.p);
+    LAUNCH(ctx, k_user_sum, cdiv(U, 128), 128, 0, ctx->rowptr.p, ctx->s_score.p, U,
+           ctx->use_ext ? ctx->ext_usum.p : (const double*)nullptr, ctx->usum.p, ctx->counters.p + 1, ctx->flags.p);
+
+    // ---------------- sort #2 (item, user rank) -> CSC ----------------
+    ctx->src_a.need(m); ctx->csc_src.need(m); ctx->keys_c.need(m);
+    LAUNCH(ctx, k_make_keys2, cdiv(m, 256), 256, 0, keys, m, item_bits, rank_bits, ctx->keys_a.p, ctx->src_a.p);
+    {
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->keys_a.p, ctx->keys_c.p, ctx->src_a.p, ctx->csc_src.p,
+                                           (int64_t)m, 0, std::min(64, item_bits + rank_bits), st));
+        ctx->cub_tmp.need(tmp);
+        CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, ctx->keys_a.p, ctx->keys_c.p, ctx->src_a.p, ctx->csc_src.p,
+                                           (int64_t)m, 0, std::min(64, item_bits + rank_bits), st));
+    }
+    const uint64_t* keys2 = ctx->keys_c.p;                   // sorted (item, rank)
+
+    const size_t tab = (size_t)KC * TI;
+    ctx->ifirst.need(TI); ctx->ilast.need(TI); ctx->tstart.need(tab); ctx->tend.need(tab); ctx->tloc.need(tab);
+    ctx->isum.need(TI); ctx->iprob.need(TI); ctx->bvec.need(TI); ctx->total.need(1);
+    ctx->icount.need(KC); ctx->item_off.need((size_t)KC + 1);
+    CK(cudaMemsetAsync(ctx->ifirst.p, 0, (size_t)TI * 4, st));
+    CK(cudaMemsetAsync(ctx->ilast.p, 0, (size_t)TI * 4, st));
+    CK(cudaMemsetAsync(ctx->tstart.p, 0xff, tab * 4, st));
+    LAUNCH(ctx, k_item_groups, cdiv(m, 256), 256, 0, keys2, m, rank_bits, ctx->rank_cluster.p, TI,
+           ctx->ifirst.p, ctx->ilast.p, ctx->tstart.p, ctx->tend.p);
+    LAUNCH(ctx, k_item_prob, cdiv(TI, 128), 128, 0, ctx->ifirst.p, ctx->ilast.p, ctx->csc_src.p, ctx->s_score.p, TI,
+           ctx->counters.p + 1, ctx->use_ext ? ctx->ext_iprob.p : (const double*)nullptr, lambda,
+           ctx->isum.p, ctx->iprob.p, ctx->bvec.p, ctx->total.p, ctx->counters.p + 2);
+    LAUNCH(ctx, k_cluster_item_count, KC, 256, 0, ctx->tstart.p, TI, ctx->icount.p);
+    LAUNCH(ctx, k_cluster_offsets, 1, 32, 0, ctx->icount.p, KC, ctx->item_off.p);
+
+    // per-user work for sharding
+    ctx->work.need(U); ctx->work_scan.need(U);
+    LAUNCH(ctx, k_user_work, cdiv(U, 256), 256, 0, ctx->rowptr.p, ctx->rank_cluster.p, ctx->icount.p, U, ctx->work.p);
+    if (ctx->prm.shard_count > 1) {
+        size_t tmp = 0;
+        CK(cub::DeviceScan::InclusiveSum(nullptr, tmp, ctx->work.p, ctx->work_scan.p, U, st));
+        ctx->cub_tmp.need(tmp);
+        CK(cub::DeviceScan::InclusiveSum(ctx->cub_tmp.p, tmp, ctx->work.p, ctx->work_scan.p, U, st));
+    }
+
+    // sync B: per-cluster item counts, total, flags, (work prefix)
+    ctx->h_icount.resize(KC); ctx->h_item_off.resize((size_t)KC + 1);
+    std::vector<double> h_scan;
+    CK(cudaMemcpyAsync(ctx->h_icount.data(), ctx->icount.p, (size_t)KC * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->h_item_off.data(), ctx->item_off.p, ((size_t)KC + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&ctx->h_total, ctx->total.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    unsigned long long h_bmin_bits = 0;
+    CK(cudaMemcpyAsync(&h_bmin_bits, ctx->counters.p + 2, sizeof(h_bmin_bits), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_flags, ctx->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+    if (ctx->prm.shard_count > 1) {
+        h_scan.resize(U);
+        CK(cudaMemcpyAsync(h_scan.data(), ctx->work_scan.p, (size_t)U * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    { int rc = check_flags(ctx, h_flags); if (rc != FY_OK) return rc; }
+    const int32_t n_slots = ctx->h_item_off[KC];
+
+    // shard = contiguous range of user ranks with ~equal estimated work (n_u * I_c)
+    int32_t ub = 0, ue = U;
+    if (ctx->prm.shard_count > 1) {
+        const double tot = h_scan[U - 1];
+        auto bound = [&](int r) -> int32_t {
+            if (r <= 0) return 0;
+            if (r >= ctx->prm.shard_count) return U;
+            const double target = tot * (double)r / (double)ctx->prm.shard_count;
+            return (int32_t)(std::lower_bound(h_scan.begin(), h_scan.end(), target) - h_scan.begin());
+        };
+        ub = bound(ctx->prm.shard_rank);
+        ue = bound(ctx->prm.shard_rank + 1);
+    }
+    ctx->shard_begin = ub; ctx->shard_end = ue;
+
+    // ---------------- local item numbering, d, alpha, c(u,j) ----------------
+    ctx->c_item.need(n_slots); ctx->c_start.need(n_slots); ctx->c_len.need(n_slots);
+    ctx->c_b.need(n_slots); ctx->c_alpha.need(n_slots);
+    ctx->csr_loc.need(m); ctx->csr_delta.need(m); ctx->csr_c.need(m); ctx->csc_lu.need(m); ctx->csc_delta.need(m);
+    LAUNCH(ctx, k_local_items, KC, 1024, 0, ctx->tstart.p, ctx->tend.p, TI, ctx->item_off.p, ctx->bvec.p,
+           ctx->tloc.p, ctx->c_item.p, ctx->c_start.p, ctx->c_len.p, ctx->c_b.p);
+    LAUNCH(ctx, k_delta, cdiv(m, 256), 256, 0, keys, ctx->s_score.p, m, item_bits, ctx->rank_cluster.p, ctx->usum.p,
+           ctx->bvec.p, ctx->tloc.p, TI, lambda, ctx->csr_loc.p, ctx->csr_delta.p);
+    LAUNCH(ctx, k_csc_fill, cdiv(m, 256), 256, 0, keys2, ctx->csc_src.p, m, rank_bits, ctx->rank_cluster.p, ctx->cstart.p,
+           ctx->csr_delta.p, ctx->csc_lu.p, ctx->csc_delta.p);
+    LAUNCH(ctx, k_alpha, cdiv(n_slots, 128), 128, 0, ctx->c_start.p, ctx->c_len.p, ctx->csc_delta.p, n_slots, ctx->c_alpha.p);
+    LAUNCH(ctx, k_cuj, cdiv(m, 128), 128, 0, keys, m, item_bits, ctx->rank_cluster.p, ctx->cstart.p, ctx->item_off.p,
+           ctx->csr_loc.p, ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, ctx->csc_src.p, ctx->csc_delta.p, ctx->csr_c.p);
+    CK(cudaEventRecord(ev_index, st));
+
+    // ---------------- exponent-peel period L from a lower bound on t ----------------
+    // t >= (K-1) * b_i * b_j >= b_min^2 (b_min = smallest positive b_i, reduced on the device) and
+    // t <= K < 2^31: L factors must stay inside the double range.  b_min = 0 (lambda = 0) -> L = 1,
+    // the variant that also handles t = 0 (log 0 = -inf, as Math.log does).
+    int L = 1;
+    {
+        double b_min = 0.0;
+        if (h_bmin_bits != ~0ull) std::memcpy(&b_min, &h_bmin_bits, sizeof(double));
+        if (b_min > 0.0 && std::isfinite(b_min)) {
+            const double neg_log2 = std::max(-2.0 * std::log2(b_min) + 2.0, 40.0);   // |log2 t| <= this
+            const int lmax = (int)std::floor(1000.0 / neg_log2);
+            L = lmax >= 8 ? 8 : lmax >= 4 ? 4 : lmax >= 2 ? 2 : 1;
+        }
+    }
+
+    // ---------------- per-cluster scoring ----------------
+    const int32_t n_rows = ue - ub;
+    int32_t max_ic = 0;
+    for (int32_t c = 0; c < KC; c++) max_ic = std::max(max_ic, ctx->h_icount[c]);
+    const int32_t out_stride = std::max(1, std::min(ctx->prm.top_n, max_ic));
+    if (out_stride > TOPN_MAX_SELECT)
+        return ctx->fail(FY_E_UNSUPPORTED, "min(numberOfRecommendations, items per cluster) = %d exceeds %d", out_stride, TOPN_MAX_SELECT);
+    ctx->out_stride = out_stride;
+    ctx->out_item.need((size_t)std::max(n_rows, 1) * out_stride);
+    ctx->out_score.need((size_t)std::max(n_rows, 1) * out_stride);
+    ctx->out_count.need((size_t)std::max(n_rows, 1) + 1);
+    ctx->out_off.need((size_t)std::max(n_rows, 1) + 1);
+    CK(cudaMemsetAsync(ctx->out_count.p, 0, ((size_t)std::max(n_rows, 1) + 1) * 4, st));
+    const double log_items = std::log((double)ctx->prm.number_of_items);   // AbstractRM2Reducer.java:328
+
+    // timeline: every mark opens a segment of the given kind; elapsed time goes to that kind
+    enum { SEG_GRAM = 0, SEG_SCORE = 1, SEG_TOPN = 2, SEG_END = 3 };
+    std::vector<std::pair<int, size_t>> marks;
+    auto mark = [&](int kind) { CK(cudaEventRecord(ctx->ev(evi), st)); marks.emplace_back(kind, evi); evi++; };
+    const size_t SCORE_BUF_BYTES = (size_t)2 << 30;
+    for (int32_t c = 0; c < KC; c++) {
+        const int32_t cs = ctx->h_cstart[c], ce = ctx->h_cstart[c + 1];
+        const int32_t r0 = std::max(cs, ub), r1 = std::min(ce, ue);
+        if (r1 <= r0) continue;
+        const int32_t K_c = ce - cs, I_c = ctx->h_icount[c], slot0 = ctx->h_item_off[c];
+        if (I_c <= 0) continue;
+        const int32_t ld = cdiv(I_c, SCORE_TILE) * SCORE_TILE;
+        const int32_t nchunk = cdiv(I_c, H_MAX_CHUNK);
+        const int32_t chunk_w = cdiv(cdiv(I_c, nchunk), 32) * 32;
+        ctx->prof.gram_bytes += (double)I_c * ld * 8.0;
+        ctx->H.need((size_t)I_c * ld);
+        ctx->chunk_ptr.need((size_t)K_c * (nchunk + 1));
+        mark(SEG_GRAM);
+        LAUNCH(ctx, k_chunk_ptr, cdiv((int64_t)K_c * (nchunk + 1), 256), 256, 0, cs, K_c, nchunk, chunk_w,
+               ctx->rowptr.p, ctx->csr_loc.p, ctx->chunk_ptr.p);
+        {
+            const size_t smem = (size_t)chunk_w * sizeof(double);
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_build_H, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LAUNCH(ctx, k_build_H, dim3(I_c, nchunk), H_THREADS, smem, I_c, ld, chunk_w, nchunk, slot0,
+                   ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, ctx->c_alpha.p, ctx->csc_lu.p, ctx->csc_delta.p,
+                   ctx->chunk_ptr.p, ctx->csr_loc.p, ctx->csr_delta.p, ctx->H.p);
+        }
+        const double log_K = std::log((double)K_c);                        // :329
+        const int32_t batch = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)(r1 - r0), SCORE_BUF_BYTES / ((size_t)ld * 8)));
+        ctx->scores.need((size_t)batch * ld);
+        int P2 = 1; while (P2 < std::min(ctx->prm.top_n, I_c)) P2 <<= 1;
+        const size_t topn_smem = (size_t)P2 * 12;
+        if (topn_smem > 40 * 1024) CK(cudaFuncSetAttribute(k_topn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topn_smem));
+        for (int32_t b0 = r0; b0 < r1; b0 += batch) {
+            const int32_t nb = std::min(batch, r1 - b0);
+            const dim3 grid(nb, ld / SCORE_TILE);
+            mark(SEG_SCORE);
+            switch (L) {
+                case 8: launch_score<8>(ctx, grid, ctx->H.p, I_c, ld, b0, slot0, log_items, log_K); break;
+                case 4: launch_score<4>(ctx, grid, ctx->H.p, I_c, ld, b0, slot0, log_items, log_K); break;
+                case 2: launch_score<2>(ctx, grid, ctx->H.p, I_c, ld, b0, slot0, log_items, log_K); break;
+                default: launch_score<1>(ctx, grid, ctx->H.p, I_c, ld, b0, slot0, log_items, log_K); break;
+            }
+            ctx->prof.score_launches++;
+            mark(SEG_TOPN);
+            LAUNCH(ctx, k_topn, nb, TOPN_THREADS, topn_smem, ctx->scores.p, I_c, ld, b0, slot0, ctx->prm.top_n, out_stride,
+                   ctx->prm.filter_users, ctx->split, ctx->n_splits, ctx->rank_userid.p, ctx->c_item.p,
+                   b0 - ub, ctx->out_item.p, ctx->out_score.p, ctx->out_count.p);
+        }
+        ctx->prof.clusters_touched++;
+    }
+    mark(SEG_END);
+
+    // ---------------- pack ----------------
+    if (n_rows > 0) {
+        size_t tmp = 0;
+        ctx->out_cnt64.need((size_t)n_rows + 1);
+        LAUNCH(ctx, k_widen_counts, cdiv(n_rows + 1, 256), 256, 0, ctx->out_count.p, n_rows + 1, ctx->out_cnt64.p);
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->out_cnt64.p, ctx->out_off.p, n_rows + 1, st));
+        ctx->cub_tmp.need(tmp);
+        CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, ctx->out_cnt64.p, ctx->out_off.p, n_rows + 1, st));
+    }
+    int64_t total_out = 0;
+    if (n_rows > 0) CK(cudaMemcpyAsync(&total_out, ctx->out_off.p + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));   // sync C: number of result triples
+    ctx->n_results = total_out;
+    ctx->p_user.need((size_t)total_out); ctx->p_item.need((size_t)total_out); ctx->p_cluster.need((size_t)total_out);
+    ctx->p_s64.need((size_t)total_out); ctx->p_s32.need((size_t)total_out);
+    if (n_rows > 0 && total_out > 0)
+        LAUNCH(ctx, k_pack, n_rows, 128, 0, ctx->out_item.p, ctx->out_score.p, ctx->out_count.p, ctx->out_off.p, out_stride,
+               ub, n_rows, ctx->rank_userid.p, ctx->rank_cluster.p, ctx->p_user.p, ctx->p_item.p, ctx->p_s64.p, ctx->p_s32.p,
+               ctx->p_cluster.p);
+    CK(cudaEventRecord(ev_end, st));
+
+    // users scored + work figures
+    std::vector<int32_t> h_count((size_t)std::max(n_rows, 1));
+    std::vector<int32_t> h_rowptr((size_t)U + 1);
+    if (n_rows > 0) CK(cudaMemcpyAsync(h_count.data(), ctx->out_count.p, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_rowptr.data(), ctx->rowptr.p, ((size_t)U + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->users_scored = 0;
+    double terms = 0.0;
+    for (int32_t r = 0; r < n_rows; r++) {
+        if (h_count[r] > 0) ctx->users_scored++;
+        const int32_t rank = ub + r;
+        terms += (double)(h_rowptr[rank + 1] - h_rowptr[rank]) * (double)ctx->h_icount[ctx->h_rank_cluster[rank]];
+    }
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev_start, ev_end)); ctx->prof.ms_total = ms;
+    CK(cudaEventElapsedTime(&ms, ev_start, ev_index)); ctx->prof.ms_index = ms;
+    for (size_t k = 0; k + 1 < marks.size(); k++) {
+        CK(cudaEventElapsedTime(&ms, ctx->ev(marks[k].second), ctx->ev(marks[k + 1].second)));
+        if (marks[k].first == SEG_GRAM) ctx->prof.ms_gram += ms;
+        else if (marks[k].first == SEG_SCORE) ctx->prof.ms_score += ms;
+        else if (marks[k].first == SEG_TOPN) ctx->prof.ms_topn += ms;
+    }
+    ctx->prof.log_terms = terms;
+    ctx->prof.score_bytes = 8.0 * terms;
+    ctx->prof.users_scored = ctx->users_scored;
+    ctx->prof.kernel_launches = ctx->launches;
+    ctx->have_results = true;
+    return FY_OK;
+}
+
+extern "C" int fy_rm2_run(fy_rm2_ctx* ctx) {
+    if (!ctx) return FY_E_ARG;
+    return guarded(ctx, [&]() { return run_pipeline(ctx); });
+}
+
+extern "C" int32_t fy_rm2_max_item(const fy_rm2_ctx* ctx) { return ctx ? ctx->max_item : -1; }
+
+extern "C" int fy_rm2_stats(fy_rm2_ctx* ctx, double* user_sum, double* item_prob, double* total) {
+    if (!ctx) return FY_E_ARG;
+    if (!ctx->have_results) return ctx->fail(FY_E_STATE, "fy_rm2_stats needs a successful fy_rm2_run");
+    return guarded(ctx, [&]() {
+        CK(cudaSetDevice(ctx->prm.device));
+        if (user_sum) {
+            std::vector<double> tmp((size_t)ctx->n_users);
+            CK(cudaMemcpyAsync(tmp.data(), ctx->usum.p, (size_t)ctx->n_users * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (int32_t k = 0; k < ctx->n_users; k++) user_sum[k] = tmp[ctx->h_input_rank[k]];
+        }
+        if (item_prob) {
+            CK(cudaMemcpyAsync(item_prob, ctx->iprob.p, ((size_t)ctx->max_item + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+        if (total) *total = ctx->h_total;
+        return (int)FY_OK;
+    });
+}
+
+extern "C" int64_t fy_rm2_result_count(const fy_rm2_ctx* ctx) { return (ctx && ctx->have_results) ? ctx->n_results : -1; }
+extern "C" int64_t fy_rm2_users_scored(const fy_rm2_ctx* ctx) { return (ctx && ctx->have_results) ? ctx->users_scored : -1; }
+
+extern "C" int fy_rm2_results(fy_rm2_ctx* ctx, int32_t* user, int32_t* item, double* score64, float* score32, int32_t* cluster) {
+    if (!ctx) return FY_E_ARG;
+    if (!ctx->have_results) return ctx->fail(FY_E_STATE, "fy_rm2_results needs a successful fy_rm2_run");
+    return guarded(ctx, [&]() {
+        CK(cudaSetDevice(ctx->prm.device));
+        const size_t n = (size_t)ctx->n_results;
+        cudaStream_t st = ctx->stream;
+        if (n) {
+            if (user) CK(cudaMemcpyAsync(user, ctx->p_user.p, n * 4, cudaMemcpyDeviceToHost, st));
+            if (item) CK(cudaMemcpyAsync(item, ctx->p_item.p, n * 4, cudaMemcpyDeviceToHost, st));
+            if (score64) CK(cudaMemcpyAsync(score64, ctx->p_s64.p, n * 8, cudaMemcpyDeviceToHost, st));
+            if (score32) CK(cudaMemcpyAsync(score32, ctx->p_s32.p, n * 4, cudaMemcpyDeviceToHost, st));
+            if (cluster) CK(cudaMemcpyAsync(cluster, ctx->p_cluster.p, n * 4, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        return (int)FY_OK;
+    });
+}
+
+extern "C" int fy_rm2_get_profile(const fy_rm2_ctx* ctx, fy_rm2_profile* out) {
+    if (!ctx || !out) return FY_E_ARG;
+    *out = ctx->prof;
+    return FY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fine seam: one AbstractRM2Reducer.reduce() group (M/rm/AbstractRM2Reducer.java:129-233)
+// ---------------------------------------------------------------------------------------------
+extern "C" int fy_rm2_score_group(fy_rm2_ctx* ctx, int32_t cluster_id, int32_t split, int32_t n_splits,
+                                  const int32_t* group_user, const double* group_user_sum, int32_t n_group_users,
+                                  const int32_t* r_user, const int32_t* r_item, const float* r_score, int64_t nnz,
+                                  const double* item_prob, int32_t max_item) {
+    if (!ctx) return FY_E_ARG;
+    if (!group_user || !group_user_sum || !r_user || !r_item || !r_score || !item_prob || n_group_users <= 0 || nnz <= 0 ||
+        n_splits <= 0 || split < 0 || split >= n_splits || cluster_id < 0 || max_item < 0)
+        return ctx->fail(FY_E_ARG, "fy_rm2_score_group: bad argument");
+    if (ctx->prm.shard_count > 1) return ctx->fail(FY_E_UNSUPPORTED, "fy_rm2_score_group on a sharded context");
+    return guarded(ctx, [&]() {
+        int rc = upload_ratings(ctx, r_user, r_item, r_score, nnz);
+        if (rc != FY_OK) return rc;
+        if (ctx->max_item > max_item) return ctx->fail(FY_E_ARG, "p(%d|C) not found (item id beyond item_prob)", ctx->max_item);  // :294-298
+        // a single cluster holding exactly the group's users; ids keep their cluster id for the sink
+        std::vector<int32_t> cl((size_t)n_group_users, 0), sz(1, n_group_users);
+        rc = upload_clustering(ctx, group_user, cl.data(), n_group_users, sz.data(), 1, true);
+        if (rc != FY_OK) return rc;
+        std::vector<double> us((size_t)n_group_users);
+        for (int32_t k = 0; k < n_group_users; k++) us[ctx->h_input_rank[k]] = group_user_sum[k];
+        ctx->ext_usum.need(n_group_users); ctx->ext_iprob.need((size_t)ctx->max_item + 1);
+        CK(cudaMemcpyAsync(ctx->ext_usum.p, us.data(), (size_t)n_group_users * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->ext_iprob.p, item_prob, ((size_t)ctx->max_item + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->use_ext = true; ctx->split = split; ctx->n_splits = n_splits;
+        rc = run_pipeline(ctx);
+        ctx->use_ext = false; ctx->split = 0; ctx->n_splits = 1;
+        ctx->have_ratings = false; ctx->have_clustering = false;   // the group replaced the coarse inputs
+        if (rc != FY_OK) return rc;
+        // report the caller's cluster id at the sink (writePreference(..., cluster), :364-365)
+        if (ctx->n_results > 0) {
+            std::vector<int32_t> cid((size_t)ctx->n_results, cluster_id);
+            CK(cudaMemcpyAsync(ctx->p_cluster.p, cid.data(), (size_t)ctx->n_results * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+        return (int)FY_OK;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// config 3 entry points live in cooc_tcgen05.cu
+// ---------------------------------------------------------------------------------------------

@@ -1,0 +1,705 @@
+// rm2_kernels.cuh -- device code of the RM2 engine (sm_100a).
+//
+// What the reference does per cluster (M/rm/AbstractRM2Reducer.java:129-233,321-371):
+//   P[v][i] = (1-lambda)*(r_vi/S_v) + lambda*p(i|C)                       (:384-389)
+//   score(u,i) = pvpi(u) + sum_{j in rated(u)} log( sum_{v != u} P[v][i]*P[v][j] )   (:332-354)
+//   top-N by descending score                                             (:358-369)
+//
+// How this engine computes the same numbers.  Write P[v][i] = b_i + d_vi with b_i = lambda*p(i|C)
+// (the exact value of P for an unrated cell) and d_vi = P[v][i] - b_i (non-zero only where v rated
+// i).  For a candidate i (unrated by u) and a rated item j of u,
+//   t(u,i,j) = sum_{v != u} P[v][i]*P[v][j] = H[j][i] + b_i * c(u,j)
+//   H[j][i]  = S[j][i] + b_j * alpha_i,   S[j][i] = sum_{v rated i and j} d_vi*d_vj,
+//   alpha_i  = sum_{v rated i} d_vi,      c(u,j)  = (K-1)*b_j + sum_{v != u, v rated j} d_vj.
+// Every term is non-negative, so nothing cancels: t carries a few ulp of error for any lambda.
+// S is built from the sparse ratings (work sum_v n_v^2, not the dense 2*I^2*K of a GEMM), H is
+// written once per cluster (I_c^2 doubles) and the score kernel streams row H[j][.] for every
+// rated j of every user: 8 bytes per (u,i,j) log-term, the HBM-bound part.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fy {
+
+// error flags raised on the device, read back at the host sync points
+enum DevFlag : int {
+    DF_UNKNOWN_USER = 0,
+    DF_DUPLICATE = 1,
+    DF_USER_WITHOUT_RATING = 2,
+    DF_BAD_ITEM = 3,
+    DF_COUNT = 8
+};
+
+constexpr int SCORE_TILE = 256;     // candidates per score CTA (2 per thread)
+constexpr int SCORE_THREADS = 128;
+constexpr int SCORE_CHUNK = 512;    // rated items staged in shared memory at a time
+constexpr int H_MAX_CHUNK = 8192;   // columns of one H row accumulated per CTA (64 KB of doubles)
+constexpr int H_THREADS = 256;
+constexpr int TOPN_THREADS = 512;
+constexpr int TOPN_MAX_SELECT = 4096;
+
+// ---------------------------------------------------------------------------------------------
+// Indexing
+// ---------------------------------------------------------------------------------------------
+
+// rating -> sort key (rank << item_bits | item); ratings with score <= 0 get the all-ones key and
+// sort to the end (the mappers drop them: M/rm/ScoreByClusterHDFSMapper.java:39-40).
+__global__ void k_make_keys(const int32_t* __restrict__ r_user, const int32_t* __restrict__ r_item,
+                            const float* __restrict__ r_score, int64_t nnz,
+                            const int32_t* __restrict__ uid_sorted, const int32_t* __restrict__ uid_rank,
+                            int32_t n_users, int item_bits, int32_t max_item_allowed,
+                            uint64_t* __restrict__ keys, unsigned long long* __restrict__ n_valid,
+                            int* __restrict__ flags) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int local_valid = 0;
+    if (e < nnz) {
+        uint64_t key = ~0ull;
+        if (r_score[e] > 0.0f) {
+            const int32_t uid = r_user[e];
+            int lo = 0, hi = n_users - 1, rank = -1;
+            while (lo <= hi) {
+                const int mid = (lo + hi) >> 1;
+                const int32_t v = uid_sorted[mid];
+                if (v == uid) { rank = uid_rank[mid]; break; }
+                if (v < uid) lo = mid + 1; else hi = mid - 1;
+            }
+            const int32_t it = r_item[e];
+            if (rank < 0) {
+                atomicOr(&flags[DF_UNKNOWN_USER], 1);
+            } else if (it < 0 || it > max_item_allowed) {
+                atomicOr(&flags[DF_BAD_ITEM], 1);
+            } else {
+                key = ((uint64_t)(uint32_t)rank << item_bits) | (uint64_t)(uint32_t)it;
+                local_valid = 1;
+            }
+        }
+        keys[e] = key;
+    }
+    const int block_valid = __syncthreads_count(local_valid);
+    if (threadIdx.x == 0 && block_valid) atomicAdd(n_valid, (unsigned long long)block_valid);
+}
+
+// set_ratings-time scan: largest item id among positive ratings, negative ids flagged
+__global__ void k_scan_ratings(const int32_t* __restrict__ r_item, const float* __restrict__ r_score, int64_t nnz,
+                               int* __restrict__ max_item, int* __restrict__ flags) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int local_max = -1;
+    if (e < nnz && r_score[e] > 0.0f) {
+        local_max = r_item[e];
+        if (local_max < 0) { atomicOr(&flags[DF_BAD_ITEM], 1); local_max = -1; }
+    }
+    for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+    if ((threadIdx.x & 31) == 0 && local_max >= 0) atomicMax(max_item, local_max);
+}
+
+// sorted keys -> CSR row pointers over user ranks (+ duplicate detection)
+__global__ void k_rows(const uint64_t* __restrict__ keys, int32_t m, int item_bits, int32_t n_users,
+                       int32_t* __restrict__ rowptr, int* __restrict__ flags) {
+    const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    const uint64_t k = keys[e];
+    const int32_t r = (int32_t)(k >> item_bits);
+    int32_t prev = -1;
+    if (e > 0) {
+        const uint64_t kp = keys[e - 1];
+        prev = (int32_t)(kp >> item_bits);
+        if (kp == k) atomicOr(&flags[DF_DUPLICATE], 1);
+    }
+    for (int32_t q = prev + 1; q <= r; q++) rowptr[q] = e;
+    if (e == m - 1)
+        for (int32_t q = r + 1; q <= n_users; q++) rowptr[q] = m;
+}
+
+// RM2-1: user sums in ascending item order (M/rm/DoubleSumReducer.java:31-42) and the truncated
+// counter += (long) sum * 100 (M/rm/DoubleSumAndCountReducer.java:41).
+__global__ void k_user_sum(const int32_t* __restrict__ rowptr, const float* __restrict__ s_score,
+                           int32_t n_users, const double* __restrict__ ext_usum,
+                           double* __restrict__ usum, unsigned long long* __restrict__ counter,
+                           int* __restrict__ flags) {
+    const int32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_users) return;
+    const int32_t e0 = rowptr[u], e1 = rowptr[u + 1];
+    if (e1 <= e0) { atomicOr(&flags[DF_USER_WITHOUT_RATING], 1); usum[u] = 0.0; return; }
+    double s = 0.0;
+    for (int32_t e = e0; e < e1; e++) s = __dadd_rn(s, (double)s_score[e]);
+    if (ext_usum) s = ext_usum[u];
+    usum[u] = s;
+    atomicAdd(counter, (unsigned long long)((long long)s) * 100ull);
+}
+
+// second sort key: item << rank_bits | rank  (CSC order: item-major, then (cluster,user) rank)
+__global__ void k_make_keys2(const uint64_t* __restrict__ keys, int32_t m, int item_bits, int rank_bits,
+                             uint64_t* __restrict__ keys2, int32_t* __restrict__ src) {
+    const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    const uint64_t k = keys[e];
+    const uint64_t item = k & ((1ull << item_bits) - 1);
+    const uint64_t rank = k >> item_bits;
+    keys2[e] = (item << rank_bits) | rank;
+    src[e] = e;
+}
+
+// CSC boundaries: per item [ifirst, ilast) and per (cluster, item) group [tstart, tend)
+__global__ void k_item_groups(const uint64_t* __restrict__ keys2, int32_t m, int rank_bits,
+                              const int32_t* __restrict__ rank_cluster, int32_t table_items,
+                              int32_t* __restrict__ ifirst, int32_t* __restrict__ ilast,
+                              int32_t* __restrict__ tstart, int32_t* __restrict__ tend) {
+    const int32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= m) return;
+    const uint64_t rmask = (1ull << rank_bits) - 1;
+    const uint64_t k = keys2[x];
+    const int32_t item = (int32_t)(k >> rank_bits);
+    const int32_t c = rank_cluster[(int32_t)(k & rmask)];
+    int32_t pitem = -1, pc = -1, nitem = -1, nc = -1;
+    if (x > 0) { const uint64_t kp = keys2[x - 1]; pitem = (int32_t)(kp >> rank_bits); pc = rank_cluster[(int32_t)(kp & rmask)]; }
+    if (x < m - 1) { const uint64_t kn = keys2[x + 1]; nitem = (int32_t)(kn >> rank_bits); nc = rank_cluster[(int32_t)(kn & rmask)]; }
+    const size_t t = (size_t)c * table_items + item;
+    if (item != pitem) ifirst[item] = x;
+    if (item != nitem) ilast[item] = x + 1;
+    if (item != pitem || c != pc) tstart[t] = x;
+    if (item != nitem || c != nc) tend[t] = x + 1;
+}
+
+// RM2-2: item sums in ascending (cluster,user) order, p(i|C) = sum / total
+// (M/rm/DoubleSumAndDividerReducer.java:32-46), b_i = lambda * p(i|C).
+__global__ void k_item_prob(const int32_t* __restrict__ ifirst, const int32_t* __restrict__ ilast,
+                            const int32_t* __restrict__ csc_src, const float* __restrict__ s_score,
+                            int32_t table_items, const unsigned long long* __restrict__ counter,
+                            const double* __restrict__ ext_iprob, double lambda,
+                            double* __restrict__ isum, double* __restrict__ iprob, double* __restrict__ bvec,
+                            double* __restrict__ total_out, unsigned long long* __restrict__ bmin_bits) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double total = __ddiv_rn((double)(long long)(*counter), 100.0);   // RM2Job.java:95
+    if (i == 0) *total_out = total;
+    if (i >= table_items) return;
+    const int32_t x0 = ifirst[i], x1 = ilast[i];
+    double s = 0.0;
+    for (int32_t x = x0; x < x1; x++) s = __dadd_rn(s, (double)s_score[csc_src[x]]);
+    double p = (x1 > x0) ? __ddiv_rn(s, total) : 0.0;
+    if (ext_iprob) p = ext_iprob[i];
+    isum[i] = s;
+    iprob[i] = p;
+    const double b = __dmul_rn(lambda, p);
+    bvec[i] = b;
+    // smallest b over rated items (positive doubles order like their bit patterns); 0 if any b is 0
+    if (x1 > x0) atomicMin(bmin_bits, (unsigned long long)__double_as_longlong(b > 0.0 ? b : 0.0));
+}
+
+// number of distinct items of each cluster
+__global__ void k_cluster_item_count(const int32_t* __restrict__ tstart, int32_t table_items,
+                                     int32_t* __restrict__ icount) {
+    const int c = blockIdx.x;
+    int cnt = 0;
+    for (int32_t i = threadIdx.x; i < table_items; i += blockDim.x) cnt += (tstart[(size_t)c * table_items + i] >= 0);
+    __shared__ int s_total;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_total, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) icount[c] = s_total;
+}
+
+// exclusive scan over clusters (tiny) -> item_off; also total
+__global__ void k_cluster_offsets(const int32_t* __restrict__ icount, int32_t n_clusters,
+                                  int32_t* __restrict__ item_off) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int32_t acc = 0;
+        for (int c = 0; c < n_clusters; c++) { item_off[c] = acc; acc += icount[c]; }
+        item_off[n_clusters] = acc;
+    }
+}
+
+// local item numbering per cluster: ascending item id (items[] of createUserAndItemMappings,
+// M/rm/AbstractRM2Reducer.java:238-272, canonicalised), plus the per-slot tables.
+__global__ void k_local_items(const int32_t* __restrict__ tstart, const int32_t* __restrict__ tend,
+                              int32_t table_items, const int32_t* __restrict__ item_off,
+                              const double* __restrict__ bvec,
+                              int32_t* __restrict__ tloc, int32_t* __restrict__ c_item,
+                              int32_t* __restrict__ c_start, int32_t* __restrict__ c_len,
+                              double* __restrict__ c_b) {
+    const int c = blockIdx.x;
+    const int T = blockDim.x;  // 1024
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int32_t i0 = 0; i0 < table_items; i0 += T) {
+        const int32_t i = i0 + threadIdx.x;
+        const size_t t = (size_t)c * table_items + (i < table_items ? i : 0);
+        const int32_t st = (i < table_items) ? tstart[t] : -1;
+        const int f = st >= 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        const int inwarp = __popc(bal & ((1u << lane) - 1));
+        if (lane == 0) s_warp[w] = __popc(bal);
+        __syncthreads();
+        int wbase = 0;
+        for (int q = 0; q < w; q++) wbase += s_warp[q];
+        int tot = 0;
+        for (int q = 0; q < (T >> 5); q++) tot += s_warp[q];
+        const int base = s_base;
+        if (f) {
+            const int32_t l = base + wbase + inwarp;
+            tloc[t] = l;
+            const int32_t slot = item_off[c] + l;
+            c_item[slot] = i;
+            c_start[slot] = st;
+            c_len[slot] = tend[t] - st;
+            c_b[slot] = bvec[i];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = base + tot;
+        __syncthreads();
+    }
+}
+
+// CSR entry -> local item id, d_vi = P[v][i] - b_i with P rounded exactly as
+// probItemGivenUser does: (1 - lambda) * (rating / sum) + lambda * p   (:384-389, no FMA).
+__global__ void k_delta(const uint64_t* __restrict__ keys, const float* __restrict__ s_score, int32_t m,
+                        int item_bits, const int32_t* __restrict__ rank_cluster,
+                        const double* __restrict__ usum, const double* __restrict__ bvec,
+                        const int32_t* __restrict__ tloc, int32_t table_items, double lambda,
+                        int32_t* __restrict__ csr_loc, double* __restrict__ csr_delta) {
+    const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    const uint64_t k = keys[e];
+    const int32_t item = (int32_t)(k & ((1ull << item_bits) - 1));
+    const int32_t rank = (int32_t)(k >> item_bits);
+    const int32_t c = rank_cluster[rank];
+    const double b = bvec[item];
+    const double oml = __dsub_rn(1.0, lambda);
+    const double q = __dmul_rn(oml, __ddiv_rn((double)s_score[e], usum[rank]));
+    const double P = __dadd_rn(q, b);
+    csr_loc[e] = tloc[(size_t)c * table_items + item];
+    csr_delta[e] = __dsub_rn(P, b);
+}
+
+// CSC side copies: local user index and d for every CSC position
+__global__ void k_csc_fill(const uint64_t* __restrict__ keys2, const int32_t* __restrict__ csc_src, int32_t m,
+                           int rank_bits, const int32_t* __restrict__ rank_cluster,
+                           const int32_t* __restrict__ cstart, const double* __restrict__ csr_delta,
+                           int32_t* __restrict__ csc_lu, double* __restrict__ csc_delta) {
+    const int32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= m) return;
+    const int32_t rank = (int32_t)(keys2[x] & ((1ull << rank_bits) - 1));
+    csc_lu[x] = rank - cstart[rank_cluster[rank]];
+    csc_delta[x] = csr_delta[csc_src[x]];
+}
+
+// alpha per (cluster, local item): sum of d over the raters, ascending user
+__global__ void k_alpha(const int32_t* __restrict__ c_start, const int32_t* __restrict__ c_len,
+                        const double* __restrict__ csc_delta, int32_t n_slots, double* __restrict__ c_alpha) {
+    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    const int32_t x0 = c_start[s], n = c_len[s];
+    double a = 0.0;
+    for (int32_t r = 0; r < n; r++) a = __dadd_rn(a, csc_delta[x0 + r]);
+    c_alpha[s] = a;
+}
+
+// c(u,j) = (K-1)*b_j + sum_{v != u, v rated j} d_vj   for every CSR entry (u,j)
+__global__ void k_cuj(const uint64_t* __restrict__ keys, int32_t m, int item_bits,
+                      const int32_t* __restrict__ rank_cluster, const int32_t* __restrict__ cstart,
+                      const int32_t* __restrict__ item_off, const int32_t* __restrict__ csr_loc,
+                      const int32_t* __restrict__ c_start, const int32_t* __restrict__ c_len,
+                      const double* __restrict__ c_b, const int32_t* __restrict__ csc_src,
+                      const double* __restrict__ csc_delta, double* __restrict__ csr_c) {
+    const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    const int32_t rank = (int32_t)(keys[e] >> item_bits);
+    const int32_t c = rank_cluster[rank];
+    const int32_t K = cstart[c + 1] - cstart[c];
+    const int32_t slot = item_off[c] + csr_loc[e];
+    const int32_t x0 = c_start[slot], n = c_len[slot];
+    double a = 0.0;
+    for (int32_t r = 0; r < n; r++) {
+        const int32_t x = x0 + r;
+        if (csc_src[x] != e) a = __dadd_rn(a, csc_delta[x]);
+    }
+    csr_c[e] = __dadd_rn(__dmul_rn((double)(K - 1), c_b[slot]), a);
+}
+
+// per-user work estimate n_u * I_c (for sharding) as double
+__global__ void k_user_work(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rank_cluster,
+                            const int32_t* __restrict__ icount, int32_t n_users, double* __restrict__ work) {
+    const int32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_users) return;
+    work[u] = (double)(rowptr[u + 1] - rowptr[u]) * (double)icount[rank_cluster[u]];
+}
+
+// ---------------------------------------------------------------------------------------------
+// H[j][i] = S[j][i] + b_j * alpha_i   for one cluster.  One CTA per (row j, column chunk).
+// The row accumulates in shared memory; raters of j are visited in ascending user order and each
+// rater's own rated items (sorted) are scattered by distinct threads, so the sum order -- hence
+// every bit of H -- is fixed, and two identical item columns give identical H columns (exact ties
+// stay exact ties, as in the reference's double loop).
+// ---------------------------------------------------------------------------------------------
+// first CSR entry of every (user, column chunk) of one cluster: removes the per-rater binary
+// searches from k_build_H
+__global__ void k_chunk_ptr(int32_t rank0, int32_t K_c, int32_t nchunk, int32_t chunk_w,
+                            const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_loc,
+                            int32_t* __restrict__ chunk_ptr) {
+    const int32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K_c * (nchunk + 1)) return;
+    const int32_t u = idx / (nchunk + 1), q = idx % (nchunk + 1);
+    int32_t a = rowptr[rank0 + u], b = rowptr[rank0 + u + 1];
+    const int32_t target = q * chunk_w;
+    while (a < b) { const int32_t mid = (a + b) >> 1; if (csr_loc[mid] < target) a = mid + 1; else b = mid; }
+    chunk_ptr[idx] = a;
+}
+
+__global__ void __launch_bounds__(H_THREADS)
+k_build_H(int32_t I_c, int32_t ld, int32_t chunk_w, int32_t nchunk, int32_t slot0,
+          const int32_t* __restrict__ c_start, const int32_t* __restrict__ c_len,
+          const double* __restrict__ c_b, const double* __restrict__ c_alpha,
+          const int32_t* __restrict__ csc_lu, const double* __restrict__ csc_delta,
+          const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ csr_loc,
+          const double* __restrict__ csr_delta, double* __restrict__ H) {
+    extern __shared__ double acc[];
+    __shared__ int32_t s_lo[H_THREADS], s_hi[H_THREADS];
+    __shared__ double s_d[H_THREADS];
+    const int32_t j = blockIdx.x;
+    const int32_t i0 = blockIdx.y * chunk_w;
+    const int32_t i1 = min(i0 + chunk_w, I_c);
+    const int32_t w = i1 - i0;
+    for (int32_t t = threadIdx.x; t < w; t += H_THREADS) acc[t] = 0.0;
+    const int32_t x0 = c_start[slot0 + j], nr = c_len[slot0 + j];
+    for (int32_t rb = 0; rb < nr; rb += H_THREADS) {
+        const int32_t nb = min(H_THREADS, nr - rb);
+        __syncthreads();
+        if (threadIdx.x < nb) {             // stage this batch of raters: range of their row in the chunk
+            const int32_t x = x0 + rb + threadIdx.x;
+            const int32_t lu = csc_lu[x];
+            s_d[threadIdx.x] = csc_delta[x];
+            s_lo[threadIdx.x] = chunk_ptr[lu * (nchunk + 1) + blockIdx.y];
+            s_hi[threadIdx.x] = chunk_ptr[lu * (nchunk + 1) + blockIdx.y + 1];
+        }
+        __syncthreads();
+        for (int32_t r = 0; r < nb; r++) {
+            const int32_t lo = s_lo[r], hi = s_hi[r];
+            if (hi > lo) {                  // uniform over the CTA
+                const double dvj = s_d[r];
+                for (int32_t e = lo + threadIdx.x; e < hi; e += H_THREADS) {
+                    const int32_t t = csr_loc[e] - i0;
+                    acc[t] = __dadd_rn(acc[t], __dmul_rn(dvj, csr_delta[e]));
+                }
+                __syncthreads();
+            }
+        }
+    }
+    __syncthreads();
+    const double bj = c_b[slot0 + j];
+    double* __restrict__ row = H + (size_t)j * ld;
+    for (int32_t t = threadIdx.x; t < w; t += H_THREADS)
+        row[i0 + t] = __fma_rn(bj, c_alpha[slot0 + i0 + t], acc[t]);
+    if (blockIdx.y == gridDim.y - 1)
+        for (int32_t i = I_c + threadIdx.x; i < ld; i += H_THREADS) row[i] = 1.0;   // padding columns
+}
+
+// ---------------------------------------------------------------------------------------------
+// Score kernel: CTA = (user, tile of 256 candidates).  Streams H[j][tile] for every rated j.
+//   prod_i *= H[j][i] + b_i * c(u,j);   score = log(prod) + pvpi
+// The product is kept as mantissa * 2^ex; the exponent is peeled every L factors (L is chosen by
+// the host from a lower bound on t so that L factors can neither overflow nor underflow), so one
+// log per (u,i) replaces n_u logs (SURVEY.md 7.3 "log throughput").
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void peel_exponent(double& p, int& ex) {
+    const int hi = __double2hiint(p);
+    ex += (hi >> 20) - 1023;
+    p = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(p));
+}
+
+__device__ __forceinline__ double2 ld_row(const double* p) {
+    return __ldg(reinterpret_cast<const double2*>(p));
+}
+
+template <int L>
+__global__ void __launch_bounds__(SCORE_THREADS)
+k_score(const double* __restrict__ H, int32_t I_c, int32_t ld, int32_t rank_begin, int32_t slot0,
+        const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_loc,
+        const double* __restrict__ csr_c, const double* __restrict__ c_b,
+        double log_items, double log_K, double* __restrict__ scores) {
+    __shared__ int32_t s_j[SCORE_CHUNK];
+    __shared__ double s_c[SCORE_CHUNK];
+    __shared__ unsigned s_rated[SCORE_TILE / 32];
+
+    const int32_t rank = rank_begin + blockIdx.x;
+    const int32_t tile0 = blockIdx.y * SCORE_TILE;
+    const int32_t i = tile0 + 2 * threadIdx.x;
+    const int32_t e0 = rowptr[rank];
+    const int32_t n = rowptr[rank + 1] - e0;
+
+    if (threadIdx.x < SCORE_TILE / 32) s_rated[threadIdx.x] = 0u;
+    const double b0 = (i < I_c) ? c_b[slot0 + i] : 0.0;
+    const double b1 = (i + 1 < I_c) ? c_b[slot0 + i + 1] : 0.0;
+    double p0 = 1.0, p1 = 1.0;
+    int ex0 = 0, ex1 = 0;
+    bool z0 = false, z1 = false;
+    const double* __restrict__ Hc = H + i;
+
+    for (int32_t base = 0; base < n; base += SCORE_CHUNK) {
+        const int32_t cnt = min(SCORE_CHUNK, n - base);
+        __syncthreads();
+        for (int32_t k = threadIdx.x; k < cnt; k += SCORE_THREADS) {
+            const int32_t j = csr_loc[e0 + base + k];
+            s_j[k] = j;
+            s_c[k] = csr_c[e0 + base + k];
+            const int32_t d = j - tile0;
+            if (d >= 0 && d < SCORE_TILE) atomicOr(&s_rated[d >> 5], 1u << (d & 31));
+        }
+        __syncthreads();
+        int32_t k = 0;
+        for (; k + 8 <= cnt; k += 8) {
+            double2 h[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) h[q] = ld_row(Hc + (size_t)s_j[k + q] * ld);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const double c = s_c[k + q];
+                p0 *= fma(b0, c, h[q].x);
+                p1 *= fma(b1, c, h[q].y);
+                if ((q + 1) % L == 0) {
+                    if (L == 1) { if (p0 == 0.0) { z0 = true; p0 = 1.0; } if (p1 == 0.0) { z1 = true; p1 = 1.0; } }
+                    peel_exponent(p0, ex0);
+                    peel_exponent(p1, ex1);
+                }
+            }
+        }
+        for (; k < cnt; k++) {
+            const double2 h = ld_row(Hc + (size_t)s_j[k] * ld);
+            const double c = s_c[k];
+            p0 *= fma(b0, c, h.x);
+            p1 *= fma(b1, c, h.y);
+            if (L == 1) { if (p0 == 0.0) { z0 = true; p0 = 1.0; } if (p1 == 0.0) { z1 = true; p1 = 1.0; } }
+            if (L == 1 || ((k & 7) + 1) % L == 0 || k + 1 == cnt) { peel_exponent(p0, ex0); peel_exponent(p1, ex1); }
+        }
+    }
+    __syncthreads();
+    // pvpi = (n - 1) * log(numberOfItems) - n * log(K)      (AbstractRM2Reducer.java:328-329)
+    const double pvpi = __dsub_rn(__dmul_rn((double)(n - 1), log_items), __dmul_rn((double)n, log_K));
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double NANV = __longlong_as_double(0x7ff8000000000000ll);
+    const double NINF = __longlong_as_double(0xfff0000000000000ll);
+    double s0 = fma((double)ex0, LN2_HI, fma((double)ex0, LN2_LO, log(p0))) + pvpi;
+    double s1 = fma((double)ex1, LN2_HI, fma((double)ex1, LN2_LO, log(p1))) + pvpi;
+    if (z0) s0 = NINF;
+    if (z1) s1 = NINF;
+    const int d = 2 * threadIdx.x;
+    const unsigned word = s_rated[d >> 5];
+    if ((word >> (d & 31)) & 1u) s0 = NANV;
+    if ((word >> ((d + 1) & 31)) & 1u) s1 = NANV;
+    if (i >= I_c) s0 = NANV;
+    if (i + 1 >= I_c) s1 = NANV;
+    double2 out; out.x = s0; out.y = s1;
+    *reinterpret_cast<double2*>(scores + (size_t)blockIdx.x * ld + i) = out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Top-N per user: radix select on the order-preserving 64-bit image of the score, then a bitonic
+// sort of the selected (key, index) pairs.  Order = (score desc, item id asc); local index order
+// is item id order.  NaN marks "not a candidate" (rated by the user / padding).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t desc_key(double s) {
+    const uint64_t b = (uint64_t)__double_as_longlong(s);
+    const uint64_t asc = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    return ~asc;   // smaller key = larger score
+}
+__device__ __forceinline__ double key_to_score(uint64_t key) {
+    const uint64_t asc = ~key;
+    const uint64_t b = (asc >> 63) ? (asc & 0x7fffffffffffffffull) : ~asc;
+    return __longlong_as_double((long long)b);
+}
+
+__global__ void __launch_bounds__(TOPN_THREADS)
+k_topn(const double* __restrict__ scores, int32_t I_c, int32_t ld, int32_t rank_begin, int32_t slot0,
+       int32_t top_n, int32_t out_stride, int32_t filter_users, int32_t split, int32_t n_splits,
+       const int32_t* __restrict__ rank_userid, const int32_t* __restrict__ c_item,
+       int32_t out_row0, int32_t* __restrict__ out_item, double* __restrict__ out_score,
+       int32_t* __restrict__ out_count) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned long long s_red[TOPN_THREADS / 32];
+    __shared__ unsigned long long s_kmin, s_kmax;
+    __shared__ int s_cnt, s_digit, s_remaining, s_done, s_nsel, s_eqtaken;
+
+    const int32_t rank = rank_begin + blockIdx.x;
+    const int32_t orow = out_row0 + blockIdx.x;
+    const double* __restrict__ row = scores + (size_t)blockIdx.x * ld;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    const int32_t uid = rank_userid[rank];
+    if (uid < filter_users || (n_splits > 1 && (uid % n_splits) != split)) {   // :203-205, :220-223
+        if (tid == 0) out_count[orow] = 0;
+        return;
+    }
+
+    // pass 0: candidate count, min and max key
+    int cnt = 0;
+    uint64_t kmin = ~0ull, kmax = 0ull;
+    for (int32_t i = tid; i < I_c; i += TOPN_THREADS) {
+        const double s = row[i];
+        if (s == s) { const uint64_t k = desc_key(s); cnt++; kmin = min(kmin, k); kmax = max(kmax, k); }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if (tid == 0) { s_cnt = 0; s_kmin = ~0ull; s_kmax = 0ull; }
+    __syncthreads();
+    if (lane == 0) { atomicAdd(&s_cnt, cnt); atomicMin(&s_kmin, (unsigned long long)kmin); atomicMax(&s_kmax, (unsigned long long)kmax); }
+    __syncthreads();
+    const int c_u = s_cnt;
+    const int n_out = min(top_n, c_u);
+    if (n_out == 0) {                       // "does not have any unrated item in the cluster" :210-213
+        if (tid == 0) out_count[orow] = 0;
+        return;
+    }
+    const uint64_t kbase = s_kmin;
+    const uint64_t span = s_kmax - kbase;
+    // radix select on (key - kbase), 8 bits per pass from the highest set bit of the span
+    int top_bit = (span == 0) ? 0 : (64 - __clzll((long long)span));    // number of significant bits
+    uint64_t prefix = 0;       // selected high bits (value of (key-kbase) >> shift)
+    int shift = top_bit;       // bits below `shift` are still undecided
+    if (tid == 0) { s_remaining = n_out; s_done = (n_out == c_u); }
+    __syncthreads();
+    // If everything is selected (n_out == c_u) skip the select entirely.
+    while (!s_done && shift > 0) {
+        const int nshift = max(shift - 8, 0);
+        const int width = shift - nshift;
+        if (tid < 256) s_hist[tid] = 0;
+        __syncthreads();
+        for (int32_t i = tid; i < I_c; i += TOPN_THREADS) {
+            const double s = row[i];
+            if (s == s) {
+                const uint64_t d = desc_key(s) - kbase;
+                if ((shift >= 64 ? 0ull : (d >> shift)) == prefix) {
+                    const unsigned dig = (unsigned)((d >> nshift) & ((1u << width) - 1));
+                    // warp-aggregated histogram update
+                    const unsigned peers = __match_any_sync(__activemask(), dig);
+                    if ((__ffs(peers) - 1) == lane) atomicAdd(&s_hist[dig], __popc(peers));
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int rem = s_remaining, acc = 0, dsel = 0;
+            const int nb = 1 << width;
+            for (int d = 0; d < nb; d++) {
+                const int h = (int)s_hist[d];
+                if (acc + h >= rem) { dsel = d; break; }
+                acc += h;
+            }
+            s_digit = dsel;
+            s_remaining = rem - acc;                       // how many to take from bucket dsel
+            if ((int)s_hist[dsel] == rem - acc) s_done = 1; // the whole bucket is taken
+        }
+        __syncthreads();
+        prefix = (prefix << width) | (uint64_t)s_digit;
+        shift = nshift;
+        __syncthreads();
+    }
+    // Selection rule: with d = key - kbase, q = d >> shift:
+    //   q <  prefix -> selected;  q == prefix -> selected if s_done (whole bucket) else the first
+    //   s_remaining of them in index order (only reachable with shift == 0, i.e. equal keys).
+    const bool all = (n_out == c_u);
+    const bool whole_bucket = (s_done != 0);
+    const int eq_take = s_remaining;
+
+    // gather into shared memory
+    int P2 = 1; while (P2 < n_out) P2 <<= 1;
+    uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);
+    int32_t* si = reinterpret_cast<int32_t*>(smem_raw + (size_t)P2 * sizeof(uint64_t));
+    for (int t = tid; t < P2; t += TOPN_THREADS) { sk[t] = ~0ull; si[t] = 0x7fffffff; }
+    if (tid == 0) { s_nsel = 0; s_eqtaken = 0; }
+    __syncthreads();
+    for (int32_t i0 = 0; i0 < I_c; i0 += TOPN_THREADS) {
+        const int32_t i = i0 + tid;
+        bool take = false, eq = false;
+        uint64_t key = 0;
+        if (i < I_c) {
+            const double s = row[i];
+            if (s == s) {
+                key = desc_key(s);
+                if (all) take = true;
+                else {
+                    const uint64_t q = (shift >= 64) ? 0ull : ((key - kbase) >> shift);
+                    if (q < prefix) take = true;
+                    else if (q == prefix) { if (whole_bucket) take = true; else eq = true; }
+                }
+            }
+        }
+        if (!all && !whole_bucket) {
+            // ordered take of the first eq_take "equal" elements (index order = item id order)
+            const unsigned bal = __ballot_sync(0xffffffffu, eq);
+            if (lane == 0) s_red[wid] = __popc(bal);
+            __syncthreads();
+            int before = s_eqtaken;
+            for (int q = 0; q < wid; q++) before += (int)s_red[q];
+            int tot = 0;
+            for (int q = 0; q < TOPN_THREADS / 32; q++) tot += (int)s_red[q];
+            if (eq && before + __popc(bal & ((1u << lane) - 1)) < eq_take) take = true;
+            __syncthreads();
+            if (tid == 0) s_eqtaken += tot;
+            __syncthreads();
+        }
+        if (take) {
+            const int pos = atomicAdd(&s_nsel, 1);
+            if (pos < P2) { sk[pos] = key; si[pos] = i; }
+        }
+    }
+    __syncthreads();
+    // bitonic sort by (key, index)
+    for (int k = 2; k <= P2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < P2; t += TOPN_THREADS) {
+                const int ixj = t ^ j;
+                if (ixj > t) {
+                    const uint64_t ka = sk[t], kb = sk[ixj];
+                    const int32_t ia = si[t], ib = si[ixj];
+                    const bool a_gt_b = (ka > kb) || (ka == kb && ia > ib);
+                    const bool up = ((t & k) == 0);
+                    if (a_gt_b == up) { sk[t] = kb; sk[ixj] = ka; si[t] = ib; si[ixj] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = tid; t < n_out; t += TOPN_THREADS) {
+        out_item[(size_t)orow * out_stride + t] = c_item[slot0 + si[t]];
+        out_score[(size_t)orow * out_stride + t] = key_to_score(sk[t]);
+    }
+    if (tid == 0) out_count[orow] = n_out;
+}
+
+__global__ void k_widen_counts(const int32_t* __restrict__ cnt, int32_t n, int64_t* __restrict__ out) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = cnt[i];
+}
+
+// packed output
+__global__ void k_pack(const int32_t* __restrict__ out_item, const double* __restrict__ out_score,
+                       const int32_t* __restrict__ out_count, const int64_t* __restrict__ out_off,
+                       int32_t out_stride, int32_t rank_begin, int32_t n_rows,
+                       const int32_t* __restrict__ rank_userid, const int32_t* __restrict__ rank_cluster,
+                       int32_t* __restrict__ p_user, int32_t* __restrict__ p_item, double* __restrict__ p_s64,
+                       float* __restrict__ p_s32, int32_t* __restrict__ p_cluster) {
+    const int32_t r = blockIdx.x;
+    if (r >= n_rows) return;
+    const int32_t n = out_count[r];
+    const int64_t off = out_off[r];
+    const int32_t rank = rank_begin + r;
+    const int32_t uid = rank_userid[rank], c = rank_cluster[rank];
+    for (int32_t t = threadIdx.x; t < n; t += blockDim.x) {
+        const double s = out_score[(size_t)r * out_stride + t];
+        p_user[off + t] = uid;
+        p_item[off + t] = out_item[(size_t)r * out_stride + t];
+        p_s64[off + t] = s;
+        p_s32[off + t] = (float)s;                        // RM2HDFSReducer.java:48
+        p_cluster[off + t] = c;
+    }
+}
+
+}  // namespace fy

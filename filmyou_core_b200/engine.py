@@ -1,0 +1,241 @@
+"""ctypes binding of libfilmyou_rm2.so (C ABI: include/filmyou_rm2.h).
+
+The library is built in-tree by `build_library()` (called from __graft_entry__.build()) with
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
+and must be present to compute anything: there is no eager / CPU path behind this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_SO = os.path.join(_HERE, "libfilmyou_rm2.so")
+_LIB = None
+
+STATUS = {
+    0: "FY_OK", -1: "FY_E_ARG", -2: "FY_E_USER_WITHOUT_RATING", -3: "FY_E_DUPLICATE_RATING",
+    -4: "FY_E_CLUSTER_SIZE", -5: "FY_E_UNKNOWN_USER", -6: "FY_E_NOMEM", -7: "FY_E_CUDA",
+    -8: "FY_E_STATE", -9: "FY_E_UNSUPPORTED",
+}
+
+# every symbol include/filmyou_rm2.h declares
+EXPORTS = [
+    "fy_rm2_abi_version", "fy_rm2_default_params", "fy_rm2_create", "fy_rm2_destroy", "fy_rm2_last_error",
+    "fy_rm2_set_stream", "fy_rm2_set_ratings", "fy_rm2_set_clustering", "fy_rm2_run", "fy_rm2_max_item",
+    "fy_rm2_stats", "fy_rm2_result_count", "fy_rm2_users_scored", "fy_rm2_results", "fy_rm2_score_group",
+    "fy_rm2_get_profile", "fy_cooc_counts", "fy_cooc_topk",
+]
+
+
+class Rm2Error(RuntimeError):
+    """Mirrors the reference's only error convention: the job fails (M/rm/RM2Job.java:265-268)."""
+
+    def __init__(self, code, text=""):
+        super().__init__("%s (%d): %s" % (STATUS.get(code, "?"), code, text))
+        self.code = code
+
+
+class Rm2Params(C.Structure):
+    _fields_ = [("lambda_", C.c_double), ("number_of_items", C.c_int32), ("top_n", C.c_int32),
+                ("filter_users", C.c_int32), ("device", C.c_int32), ("shard_rank", C.c_int32),
+                ("shard_count", C.c_int32), ("tie_break", C.c_int32)]
+
+
+class Rm2Profile(C.Structure):
+    _fields_ = [("ms_total", C.c_double), ("ms_index", C.c_double), ("ms_gram", C.c_double),
+                ("ms_score", C.c_double), ("ms_topn", C.c_double), ("log_terms", C.c_double),
+                ("score_bytes", C.c_double), ("gram_bytes", C.c_double), ("users_scored", C.c_int64),
+                ("kernel_launches", C.c_int64), ("clusters_touched", C.c_int32), ("score_launches", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def library_path():
+    return _SO
+
+
+def sources():
+    return sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cu"))
+
+
+def build_library(force=False, verbose=False):
+    """nvcc cross-compiles for sm_100a without a GPU (seconds)."""
+    deps = sources() + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh")]
+    deps.append(os.path.join(_HERE, "..", "include", "filmyou_rm2.h"))
+    if not force and os.path.exists(_SO) and all(os.path.getmtime(d) <= os.path.getmtime(_SO) for d in deps):
+        return _SO
+    cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+           "-Xcompiler", "-fPIC", "-shared", "-o", _SO] + sources()
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return _SO
+
+
+def load_library():
+    """Load libfilmyou_rm2.so; raises (loudly) when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_SO):
+        raise Rm2Error(-7, "libfilmyou_rm2.so is missing: run __graft_entry__.build() (no CPU fallback exists)")
+    L = C.CDLL(_SO)
+    i32p, f32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_double)
+    vp = C.c_void_p
+    L.fy_rm2_abi_version.restype = C.c_int
+    L.fy_rm2_default_params.argtypes = [C.POINTER(Rm2Params)]
+    L.fy_rm2_default_params.restype = None
+    L.fy_rm2_create.argtypes = [C.POINTER(vp), C.POINTER(Rm2Params)]
+    L.fy_rm2_destroy.argtypes = [vp]
+    L.fy_rm2_destroy.restype = None
+    L.fy_rm2_last_error.argtypes = [vp]
+    L.fy_rm2_last_error.restype = C.c_char_p
+    L.fy_rm2_set_stream.argtypes = [vp, vp]
+    L.fy_rm2_set_ratings.argtypes = [vp, i32p, i32p, f32p, C.c_int64]
+    L.fy_rm2_set_clustering.argtypes = [vp, i32p, i32p, C.c_int64, i32p, C.c_int32]
+    L.fy_rm2_run.argtypes = [vp]
+    L.fy_rm2_max_item.argtypes = [vp]
+    L.fy_rm2_max_item.restype = C.c_int32
+    L.fy_rm2_stats.argtypes = [vp, f64p, f64p, f64p]
+    L.fy_rm2_result_count.argtypes = [vp]
+    L.fy_rm2_result_count.restype = C.c_int64
+    L.fy_rm2_users_scored.argtypes = [vp]
+    L.fy_rm2_users_scored.restype = C.c_int64
+    L.fy_rm2_results.argtypes = [vp, i32p, i32p, f64p, f32p, i32p]
+    L.fy_rm2_score_group.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, i32p, f64p, C.c_int32,
+                                     i32p, i32p, f32p, C.c_int64, f64p, C.c_int32]
+    L.fy_rm2_get_profile.argtypes = [vp, C.POINTER(Rm2Profile)]
+    L.fy_cooc_counts.argtypes = [vp, C.c_int32, C.c_int32, i32p, f64p]
+    L.fy_cooc_topk.argtypes = [vp, C.c_int32, i32p, i32p, i32p]
+    for name in EXPORTS:
+        getattr(L, name)
+    _LIB = L
+    return L
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Rm2Engine:
+    """One context = one GPU.  Thin, 1:1 over the C ABI."""
+
+    def __init__(self, lam=0.1, number_of_items=0, top_n=1000, filter_users=0, device=0,
+                 shard_rank=0, shard_count=1):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        p = Rm2Params()
+        self._L.fy_rm2_default_params(C.byref(p))
+        p.lambda_, p.number_of_items, p.top_n, p.filter_users = float(lam), int(number_of_items), int(top_n), int(filter_users)
+        p.device, p.shard_rank, p.shard_count = int(device), int(shard_rank), int(shard_count)
+        rc = self._L.fy_rm2_create(C.byref(self._h), C.byref(p))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise Rm2Error(rc, "fy_rm2_create failed (is a B200 visible?)")
+        self.params = p
+        self._n_users = 0
+
+    def close(self):
+        if self._h:
+            self._L.fy_rm2_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise Rm2Error(rc, self._L.fy_rm2_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._L.fy_rm2_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_ratings(self, user, item, score):
+        user, item = _i32(user), _i32(item)
+        score = np.ascontiguousarray(score, dtype=np.float32)
+        self._check(self._L.fy_rm2_set_ratings(self._h, _ptr(user, C.c_int32), _ptr(item, C.c_int32),
+                                                _ptr(score, C.c_float), len(user)))
+
+    def set_clustering(self, user, cluster, cluster_size):
+        user, cluster, cluster_size = _i32(user), _i32(cluster), _i32(cluster_size)
+        self._n_users = len(user)
+        self._check(self._L.fy_rm2_set_clustering(self._h, _ptr(user, C.c_int32), _ptr(cluster, C.c_int32),
+                                                   len(user), _ptr(cluster_size, C.c_int32), len(cluster_size)))
+
+    def run(self):
+        self._check(self._L.fy_rm2_run(self._h))
+
+    def stats(self):
+        """(user_sum in set_clustering order, item_prob by item id, total)"""
+        mi = self._L.fy_rm2_max_item(self._h)
+        us = np.zeros(self._n_users, np.float64)
+        ip = np.zeros(mi + 1, np.float64)
+        tot = C.c_double(0)
+        self._check(self._L.fy_rm2_stats(self._h, _ptr(us, C.c_double), _ptr(ip, C.c_double), C.byref(tot)))
+        return us, ip, tot.value
+
+    def result_count(self):
+        return int(self._L.fy_rm2_result_count(self._h))
+
+    def users_scored(self):
+        return int(self._L.fy_rm2_users_scored(self._h))
+
+    def results(self, out=None):
+        """dict(user, item, score64, score32, cluster) of packed triples; `out` may hold preallocated
+        (e.g. pinned) arrays of at least result_count() entries."""
+        n = self.result_count()
+        if n < 0:
+            raise Rm2Error(-8, "no results")
+        if out is None:
+            out = dict(user=np.empty(n, np.int32), item=np.empty(n, np.int32), score64=np.empty(n, np.float64),
+                       score32=np.empty(n, np.float32), cluster=np.empty(n, np.int32))
+        self._check(self._L.fy_rm2_results(self._h, _ptr(out["user"], C.c_int32), _ptr(out["item"], C.c_int32),
+                                            _ptr(out["score64"], C.c_double), _ptr(out["score32"], C.c_float),
+                                            _ptr(out["cluster"], C.c_int32)))
+        return {k: v[:n] for k, v in out.items()}
+
+    def score_group(self, cluster_id, split, n_splits, group_user, group_user_sum, r_user, r_item, r_score, item_prob):
+        group_user, r_user, r_item = _i32(group_user), _i32(r_user), _i32(r_item)
+        group_user_sum = np.ascontiguousarray(group_user_sum, dtype=np.float64)
+        r_score = np.ascontiguousarray(r_score, dtype=np.float32)
+        item_prob = np.ascontiguousarray(item_prob, dtype=np.float64)
+        self._check(self._L.fy_rm2_score_group(
+            self._h, int(cluster_id), int(split), int(n_splits), _ptr(group_user, C.c_int32),
+            _ptr(group_user_sum, C.c_double), len(group_user), _ptr(r_user, C.c_int32), _ptr(r_item, C.c_int32),
+            _ptr(r_score, C.c_float), len(r_user), _ptr(item_prob, C.c_double), len(item_prob) - 1))
+
+    def profile(self):
+        p = Rm2Profile()
+        self._check(self._L.fy_rm2_get_profile(self._h, C.byref(p)))
+        return p.as_dict()
+
+    def cooc_counts(self, n_user_ids, n_items, want_counts=True):
+        out = np.zeros((n_items, n_items), np.int32) if want_counts else None
+        ms = C.c_double(0)
+        self._check(self._L.fy_cooc_counts(self._h, int(n_user_ids), int(n_items),
+                                            _ptr(out, C.c_int32) if want_counts else None, C.byref(ms)))
+        return out, ms.value
+
+    def cooc_topk(self, n_items, k):
+        items = np.zeros((n_items, k), np.int32)
+        counts = np.zeros((n_items, k), np.int32)
+        n = np.zeros(n_items, np.int32)
+        self._check(self._L.fy_cooc_topk(self._h, int(k), _ptr(items, C.c_int32), _ptr(counts, C.c_int32), _ptr(n, C.c_int32)))
+        return items, counts, n

@@ -1,0 +1,158 @@
+/*
+ * filmyou_rm2.h -- C ABI of the B200-native RM2 engine (libfilmyou_rm2.so).
+ *
+ * Drop-in boundary for filmyou-core's job chain RM2-1..3.  The reference exposes no FFI of its
+ * own (it is 100 % Java), so each entry point below names the reference interface it replaces.
+ * M/ = /root/reference/src/main/java/es/udc/fi/dc/irlab/.
+ *
+ *   coarse seam: RM2Job.run                         M/rm/RM2Job.java:76-100
+ *       fy_rm2_set_ratings    <- the ratings SequenceFile<IntPairWritable(user,item), FloatWritable>
+ *                                read by the three mappers (M/rm/RM2Job.java:118-133,170-185,220-235)
+ *       fy_rm2_set_clustering <- DistributedCache files [0] clustering, [1] clusteringCount
+ *                                (M/rm/RM2Job.java:260-263; M/common/AbstractByClusterMapper.java:47-68;
+ *                                 M/rm/AbstractRM2Reducer.java:93-105)
+ *       fy_rm2_run            <- runUserSum + runItemColl + runItemRecommendation
+ *                                (M/rm/RM2Job.java:110-151,164-205,214-270) i.e. every
+ *                                AbstractRM2Reducer.reduce call (M/rm/AbstractRM2Reducer.java:129-233)
+ *       fy_rm2_stats          <- rm2/userSum and rm2/itemColl outputs (M/rm/RM2Job.java:138-142,190-196)
+ *       fy_rm2_results        <- every writePreference(userId, itemId, score, cluster) call
+ *                                (M/rm/AbstractRM2Reducer.java:358-369,405-407; sinks
+ *                                 M/rm/RM2HDFSReducer.java:44-50, M/rm/RM2CassandraReducer.java:49-63)
+ *   fine seam: one AbstractRM2Reducer.reduce(key, values) call
+ *       fy_rm2_score_group    <- M/rm/AbstractRM2Reducer.java:129-233 for one "c" or "c-split-nSplits" group
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; callable from JNI (GetDirectBufferAddress), Panama FFM
+ *     (MemorySegment) or ctypes.  No C++/torch types cross the boundary.
+ *   - Every function returns FY_OK (0) or a negative fy_status; fy_rm2_last_error() gives the text.
+ *     Nothing throws or aborts across the boundary (the reference's only convention is
+ *     "throw RuntimeException => task fails", M/rm/RM2Job.java:265-268).
+ *   - The caller owns every buffer it passes; inputs are copied during the call, never retained.
+ *   - A context is single-caller; distinct contexts are independent.  One context drives one GPU.
+ *   - There is NO CPU fallback: without a usable CUDA device fy_rm2_create fails with FY_E_CUDA.
+ *
+ * Ordering contract: the reference leaves the order among equal scores to
+ * java.util.PriorityQueue + hash iteration order.  This engine emits, per user, descending score
+ * with ties broken by ascending item id -- the total order of the reference's Cassandra sink
+ * (T/util/CassandraUtils.java:144-147).  Users are emitted grouped by (cluster, user id).
+ */
+#ifndef FILMYOU_RM2_H
+#define FILMYOU_RM2_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FY_RM2_ABI_VERSION 1
+
+typedef enum fy_status {
+    FY_OK = 0,
+    FY_E_ARG = -1,                  /* null pointer, negative size, id out of range                  */
+    FY_E_USER_WITHOUT_RATING = -2,  /* clustering lists a user with no positive rating; the reducer  */
+                                    /* would mis-parse the group (AbstractRM2Reducer.java:153-160)   */
+    FY_E_DUPLICATE_RATING = -3,     /* same (user,item) twice: HashMap.put order is shuffle-defined  */
+    FY_E_CLUSTER_SIZE = -4,         /* clusteringCount[c] != #users mapped to c                      */
+    FY_E_UNKNOWN_USER = -5,         /* positive rating of a user absent from `clustering`            */
+    FY_E_NOMEM = -6,                /* host or device allocation failed                              */
+    FY_E_CUDA = -7,                 /* no device / CUDA runtime error (see fy_rm2_last_error)        */
+    FY_E_STATE = -8,                /* call order violated (e.g. run before set_ratings)             */
+    FY_E_UNSUPPORTED = -9           /* parameter combination not implemented                         */
+} fy_status;
+
+/* Same names / meaning as the reference's Configuration keys
+ * (M/rmrecommender/RMRecommenderDriver.java:89-120; read at M/rm/AbstractRM2Reducer.java:108-110,197). */
+typedef struct fy_rm2_params {
+    double  lambda;            /* "lambda"                   default 0.1  (:114)                   */
+    int32_t number_of_items;   /* "numberOfItems"            the configured global item count      */
+    int32_t top_n;             /* "numberOfRecommendations"  default 1000 (:95)                    */
+    int32_t filter_users;      /* "filterUsers"              default 0    (:119)                   */
+    int32_t device;            /* CUDA device ordinal                                              */
+    int32_t shard_rank;        /* this context scores shard `shard_rank` of `shard_count`          */
+    int32_t shard_count;       /*   (users partitioned by estimated work; 0/1 = everything)        */
+    int32_t tie_break;         /* 0 = canonical (score desc, item id asc); nothing else defined    */
+} fy_rm2_params;
+
+typedef struct fy_rm2_ctx fy_rm2_ctx;
+
+int fy_rm2_abi_version(void);
+void fy_rm2_default_params(fy_rm2_params* p);
+
+int fy_rm2_create(fy_rm2_ctx** out, const fy_rm2_params* p);
+void fy_rm2_destroy(fy_rm2_ctx* ctx);
+const char* fy_rm2_last_error(const fy_rm2_ctx* ctx);
+
+/* Optional: run on a caller-owned CUDA stream (a cudaStream_t passed as void*), e.g. torch's
+ * current stream.  Default is a stream owned by the context. */
+int fy_rm2_set_stream(fy_rm2_ctx* ctx, void* cuda_stream);
+
+/* COO ratings in any order with the reference's original ids; score <= 0 is ignored exactly as the
+ * mappers do (M/rm/ScoreByClusterHDFSMapper.java:39-40).  Copies host -> device. */
+int fy_rm2_set_ratings(fy_rm2_ctx* ctx, const int32_t* user, const int32_t* item, const float* score,
+                       int64_t nnz);
+
+/* `clustering` (user -> cluster, 0-based) and `clusteringCount` (cluster -> size).  n_clusters may
+ * exceed the number of non-empty clusters (T/testdata/RMTestData.java:27). */
+int fy_rm2_set_clustering(fy_rm2_ctx* ctx, const int32_t* user, const int32_t* cluster, int64_t n_users,
+                          const int32_t* cluster_size, int32_t n_clusters);
+
+/* The timed part: statistics, per-cluster matrices, scoring and top-N for this context's shard. */
+int fy_rm2_run(fy_rm2_ctx* ctx);
+
+/* rm2/userSum (in the order users were given to fy_rm2_set_clustering), rm2/itemColl
+ * (indexed by item id, 0..max_item) and the truncated global total (M/rm/RM2Job.java:95). */
+int32_t fy_rm2_max_item(const fy_rm2_ctx* ctx);
+int fy_rm2_stats(fy_rm2_ctx* ctx, double* user_sum, double* item_prob, double* total);
+
+/* Results of the last run: packed triples grouped by (cluster, user id), descending score inside a
+ * user.  Any output pointer may be NULL.  score32 is the (float) cast of the sink
+ * (M/rm/RM2HDFSReducer.java:48). */
+int64_t fy_rm2_result_count(const fy_rm2_ctx* ctx);
+int64_t fy_rm2_users_scored(const fy_rm2_ctx* ctx);
+int fy_rm2_results(fy_rm2_ctx* ctx, int32_t* user, int32_t* item, double* score64, float* score32,
+                   int32_t* cluster);
+
+/* Fine seam: one reduce() group, exactly the records the reducer receives
+ * (M/rm/AbstractRM2Reducer.java:149-174): n_group_users (user, userSum) records, then the group's
+ * rating records; item_prob is rm2/itemColl indexed by item id (size max_item+1).
+ * Only users with user % n_splits == split are scored (:203-205).  Results via fy_rm2_results. */
+int fy_rm2_score_group(fy_rm2_ctx* ctx, int32_t cluster_id, int32_t split, int32_t n_splits,
+                       const int32_t* group_user, const double* group_user_sum, int32_t n_group_users,
+                       const int32_t* r_user, const int32_t* r_item, const float* r_score, int64_t nnz,
+                       const double* item_prob, int32_t max_item);
+
+/* Work and timing of the last run, for the bench (all measured with CUDA events on the stream the
+ * kernels were launched on). */
+typedef struct fy_rm2_profile {
+    double ms_total;        /* whole fy_rm2_run                                                  */
+    double ms_index;        /* sort / CSR / CSC / statistics                                     */
+    double ms_gram;         /* per-cluster H = S + b a^T build                                   */
+    double ms_score;        /* the streaming score kernel (dominant)                             */
+    double ms_topn;         /* radix select + sort                                               */
+    double log_terms;       /* sum over scored users of n_u * I_c  (matrix elements streamed)    */
+    double score_bytes;     /* algorithmic bytes of the score kernel = 8 * log_terms             */
+    double gram_bytes;      /* bytes of H written                                                */
+    int64_t users_scored;
+    int64_t kernel_launches; /* launches of this library's own kernels inside fy_rm2_run         */
+    int32_t clusters_touched;
+    int32_t score_launches;
+} fy_rm2_profile;
+int fy_rm2_get_profile(const fy_rm2_ctx* ctx, fy_rm2_profile* out);
+
+/* ---- Config 3: item-item co-occurrence counts on the binarised ratings -------
+ * Replaces the Mahout RowSimilarityJob(CooccurrenceCountSimilarity) call at
+ * M/baselinerecommender/BaselineRecommenderJob.java:241-253.  C[i][j] = #users with both items,
+ * int32, dense [n_items x n_items] over item ids 0..n_items-1 (bit-exact integer counts; int8
+ * tcgen05 GEMM with int32 TMEM accumulators).  PARITY UNPINNED: Mahout 0.8 is not vendored. */
+int fy_cooc_counts(fy_rm2_ctx* ctx, int32_t n_user_ids, int32_t n_items, int32_t* counts_out /* host, may be NULL */,
+                   double* ms_gemm_out);
+/* per-row top-k of the last fy_cooc_counts, self excluded (maxSimilaritiesPerRow=100,
+ * excludeSelfSimilarity=true, BaselineRecommenderJob.java:247-250); ties by ascending item id. */
+int fy_cooc_topk(fy_rm2_ctx* ctx, int32_t k, int32_t* item_out /* [n_items*k] */, int32_t* count_out /* [n_items*k] */,
+                 int32_t* n_out /* [n_items] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

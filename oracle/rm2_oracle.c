@@ -1,0 +1,458 @@
+/*
+ * rm2_oracle.c -- CPU restatement of filmyou-core's RM2 hot path.  TEST INFRASTRUCTURE ONLY
+ * (see rm2_oracle.h for the contract, the reference anchors and how parity is pinned).
+ *
+ * Build (oracle/Makefile):  gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC
+ *   -ffp-contract=off : Java never fuses a*b+c; every operation below rounds to double
+ *                       exactly as M/rm/AbstractRM2Reducer.java:344,388 does.
+ */
+#include "rm2_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+struct orc_result {
+    int64_t count;
+    int64_t users_scored;
+    double seconds;
+    int32_t* user;
+    int32_t* item;
+    double* score;
+    int32_t* cluster;
+};
+
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+/* ---- a rating with its dense user index, sortable by (user index, item id) ---- */
+typedef struct {
+    int32_t uidx; /* position of the user in the (cluster, user id)-sorted user list */
+    int32_t item;
+    float score;
+} rating_t;
+
+static int cmp_rating(const void* a, const void* b) {
+    const rating_t* x = (const rating_t*)a;
+    const rating_t* y = (const rating_t*)b;
+    if (x->uidx != y->uidx) return x->uidx < y->uidx ? -1 : 1;
+    if (x->item != y->item) return x->item < y->item ? -1 : 1;
+    return 0;
+}
+
+typedef struct {
+    int32_t id;
+    int32_t cluster;
+} user_t;
+
+static int cmp_user_cluster(const void* a, const void* b) {
+    const user_t* x = (const user_t*)a;
+    const user_t* y = (const user_t*)b;
+    if (x->cluster != y->cluster) return x->cluster < y->cluster ? -1 : 1;
+    if (x->id != y->id) return x->id < y->id ? -1 : 1;
+    return 0;
+}
+
+typedef struct {
+    int32_t id;
+    int32_t idx;
+} idmap_t;
+
+static int cmp_idmap(const void* a, const void* b) {
+    const idmap_t* x = (const idmap_t*)a;
+    const idmap_t* y = (const idmap_t*)b;
+    return x->id < y->id ? -1 : (x->id > y->id ? 1 : 0);
+}
+
+static int32_t idmap_find(const idmap_t* m, int64_t n, int32_t id) {
+    int64_t lo = 0, hi = n - 1;
+    while (lo <= hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (m[mid].id == id) return m[mid].idx;
+        if (m[mid].id < id) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+
+static int cmp_i32(const void* a, const void* b) {
+    int32_t x = *(const int32_t*)a, y = *(const int32_t*)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Statistics: jobs RM2-1 (userSum + truncated total) and RM2-2 (p(i|C)).
+ * ------------------------------------------------------------------------------------------- */
+int orc_rm2_stats(const int32_t* r_user, const int32_t* r_item, const float* r_score, int64_t nnz,
+                  const int32_t* users, int64_t n_users, double* user_sum,
+                  int32_t max_item, double* item_sum, double* item_prob, double* total) {
+    if (nnz < 0 || n_users < 0 || max_item < 0) return ORC_E_ARG;
+    idmap_t* map = (idmap_t*)malloc(sizeof(idmap_t) * (size_t)(n_users > 0 ? n_users : 1));
+    if (!map) return ORC_E_NOMEM;
+    for (int64_t k = 0; k < n_users; k++) { map[k].id = users[k]; map[k].idx = (int32_t)k; }
+    qsort(map, (size_t)n_users, sizeof(idmap_t), cmp_idmap);
+    for (int64_t k = 0; k < n_users; k++) user_sum[k] = 0.0;
+    for (int32_t i = 0; i <= max_item; i++) item_sum[i] = 0.0;
+    for (int64_t e = 0; e < nnz; e++) {
+        float s = r_score[e];
+        if (!(s > 0)) continue;                          /* SimpleScoreByUserHDFSMapper.java:37-40 */
+        int32_t k = idmap_find(map, n_users, r_user[e]);
+        if (k < 0 || r_item[e] < 0 || r_item[e] > max_item) { free(map); return ORC_E_UNKNOWN_USER; }
+        user_sum[k] += (double)s;                        /* DoubleSumReducer.java:36-38 */
+        item_sum[r_item[e]] += (double)s;                /* DoubleSumAndDividerReducer.java:37-39 */
+    }
+    int64_t counter = 0;
+    for (int64_t k = 0; k < n_users; k++)
+        counter += (int64_t)user_sum[k] * 100;           /* (long) sum * OFFSET, DoubleSumAndCountReducer.java:41 */
+    double t = (double)counter / 100;                    /* RM2Job.java:95,149 */
+    *total = t;
+    for (int32_t i = 0; i <= max_item; i++)
+        item_prob[i] = item_sum[i] > 0 ? item_sum[i] / t : 0.0; /* DoubleSumAndDividerReducer.java:44 */
+    free(map);
+    return ORC_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * One scored candidate and the canonical order (score desc, item id asc).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    double score;
+    int32_t item; /* original item id */
+} cand_t;
+
+static int cmp_cand(const void* a, const void* b) {
+    const cand_t* x = (const cand_t*)a;
+    const cand_t* y = (const cand_t*)b;
+    if (x->score > y->score) return -1;                  /* IntDouble.java:31-34: Double.compare(other, this) */
+    if (x->score < y->score) return 1;
+    return x->item < y->item ? -1 : (x->item > y->item ? 1 : 0);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * The whole job: RM2-1, RM2-2 and RM2-3 (AbstractRM2Reducer.reduce per cluster).
+ * ------------------------------------------------------------------------------------------- */
+int orc_rm2_run(const orc_params* p,
+                const int32_t* r_user, const int32_t* r_item, const float* r_score, int64_t nnz,
+                const int32_t* cl_user, const int32_t* cl_cluster, int64_t n_users,
+                const int32_t* cluster_size, int32_t n_clusters,
+                const int32_t* only_users, int64_t n_only,
+                orc_result** out) {
+    if (!p || !out || nnz < 0 || n_users <= 0 || n_clusters <= 0 || p->top_n < 0) return ORC_E_ARG;
+    *out = NULL;
+    int rc = ORC_OK;
+
+    /* ---- users in (cluster, id) order: `users[]` of the reducer, canonicalised ---- */
+    user_t* us = (user_t*)malloc(sizeof(user_t) * (size_t)n_users);
+    idmap_t* map = (idmap_t*)malloc(sizeof(idmap_t) * (size_t)n_users);
+    int64_t* cstart = (int64_t*)calloc((size_t)n_clusters + 1, sizeof(int64_t));
+    rating_t* rt = (rating_t*)malloc(sizeof(rating_t) * (size_t)(nnz > 0 ? nnz : 1));
+    int64_t* rowptr = (int64_t*)calloc((size_t)n_users + 1, sizeof(int64_t));
+    double* usum = (double*)calloc((size_t)n_users, sizeof(double));
+    char* wanted = NULL;
+    double* isum = NULL;
+    double* iprob = NULL;
+    orc_result* res = NULL;
+    if (!us || !map || !cstart || !rt || !rowptr || !usum) { rc = ORC_E_NOMEM; goto done; }
+
+    for (int64_t k = 0; k < n_users; k++) {
+        us[k].id = cl_user[k];
+        us[k].cluster = cl_cluster[k];
+        if (cl_cluster[k] < 0 || cl_cluster[k] >= n_clusters) { rc = ORC_E_ARG; goto done; }
+    }
+    qsort(us, (size_t)n_users, sizeof(user_t), cmp_user_cluster);
+    for (int64_t k = 0; k < n_users; k++) {
+        map[k].id = us[k].id; map[k].idx = (int32_t)k;
+        cstart[us[k].cluster + 1]++;
+    }
+    for (int32_t c = 0; c < n_clusters; c++) {
+        if (cstart[c + 1] != cluster_size[c]) { rc = ORC_E_CLUSTER_SIZE; goto done; }
+        cstart[c + 1] += cstart[c];
+    }
+    qsort(map, (size_t)n_users, sizeof(idmap_t), cmp_idmap);
+    for (int64_t k = 1; k < n_users; k++)
+        if (map[k].id == map[k - 1].id) { rc = ORC_E_ARG; goto done; }
+
+    /* ---- positive ratings only, by (user index, item) ---- */
+    int64_t m = 0;
+    int32_t max_item = 0;
+    for (int64_t e = 0; e < nnz; e++) {
+        if (!(r_score[e] > 0)) continue;                 /* ScoreByClusterHDFSMapper.java:39-40 */
+        int32_t k = idmap_find(map, n_users, r_user[e]);
+        if (k < 0) { rc = ORC_E_UNKNOWN_USER; goto done; }
+        if (r_item[e] < 0) { rc = ORC_E_ARG; goto done; }
+        rt[m].uidx = k; rt[m].item = r_item[e]; rt[m].score = r_score[e];
+        if (r_item[e] > max_item) max_item = r_item[e];
+        m++;
+    }
+    qsort(rt, (size_t)m, sizeof(rating_t), cmp_rating);
+    for (int64_t e = 1; e < m; e++)
+        if (rt[e].uidx == rt[e - 1].uidx && rt[e].item == rt[e - 1].item) { rc = ORC_E_DUPLICATE_RATING; goto done; }
+    for (int64_t e = 0; e < m; e++) rowptr[rt[e].uidx + 1]++;
+    for (int64_t k = 0; k < n_users; k++) {
+        if (rowptr[k + 1] == 0) { rc = ORC_E_USER_WITHOUT_RATING; goto done; }
+        rowptr[k + 1] += rowptr[k];
+    }
+
+    /* ---- RM2-1: user sums (ascending item order) and the truncated total ---- */
+    int64_t counter = 0;
+    for (int64_t k = 0; k < n_users; k++) {
+        double s = 0;
+        for (int64_t e = rowptr[k]; e < rowptr[k + 1]; e++) s += (double)rt[e].score;
+        usum[k] = s;
+        counter += (int64_t)s * 100;                     /* DoubleSumAndCountReducer.java:41 */
+    }
+    const double total = (double)counter / 100;          /* RM2Job.java:95 */
+
+    /* ---- RM2-2: p(i|C), item sums accumulated in ascending (cluster,user) order ---- */
+    isum = (double*)calloc((size_t)max_item + 1, sizeof(double));
+    iprob = (double*)calloc((size_t)max_item + 1, sizeof(double));
+    if (!isum || !iprob) { rc = ORC_E_NOMEM; goto done; }
+    for (int64_t e = 0; e < m; e++) isum[rt[e].item] += (double)rt[e].score;
+    for (int32_t i = 0; i <= max_item; i++) iprob[i] = isum[i] / total; /* DoubleSumAndDividerReducer.java:44 */
+
+    /* ---- which users are scored ---- */
+    wanted = (char*)malloc((size_t)n_users);
+    if (!wanted) { rc = ORC_E_NOMEM; goto done; }
+    if (n_only > 0) {
+        memset(wanted, 0, (size_t)n_users);
+        for (int64_t k = 0; k < n_only; k++) {
+            int32_t idx = idmap_find(map, n_users, only_users[k]);
+            if (idx < 0) { rc = ORC_E_UNKNOWN_USER; goto done; }
+            wanted[idx] = 1;
+        }
+    } else {
+        memset(wanted, 1, (size_t)n_users);
+    }
+
+    res = (orc_result*)calloc(1, sizeof(orc_result));
+    if (!res) { rc = ORC_E_NOMEM; goto done; }
+    int64_t cap = 0;
+    {
+        int64_t nw = 0;
+        for (int64_t k = 0; k < n_users; k++) nw += wanted[k];
+        /* upper bound per user: min(top_n, max_item+1) */
+        int64_t per = (int64_t)max_item + 1;
+        if (p->top_n < per) per = p->top_n;
+        cap = nw * per + 1;
+    }
+    res->user = (int32_t*)malloc(sizeof(int32_t) * (size_t)cap);
+    res->item = (int32_t*)malloc(sizeof(int32_t) * (size_t)cap);
+    res->score = (double*)malloc(sizeof(double) * (size_t)cap);
+    res->cluster = (int32_t*)malloc(sizeof(int32_t) * (size_t)cap);
+    if (!res->user || !res->item || !res->score || !res->cluster) { rc = ORC_E_NOMEM; goto done; }
+
+    const double lambda = p->lambda;
+    const double log_items = log((double)p->number_of_items);   /* AbstractRM2Reducer.java:328 */
+    int threads = p->threads > 0 ? p->threads : 1;
+#ifdef _OPENMP
+    omp_set_num_threads(threads);
+#else
+    (void)threads;
+#endif
+
+    /* ---- RM2-3: one "reduce" per cluster ---- */
+    for (int32_t c = 0; c < n_clusters && rc == ORC_OK; c++) {
+        const int64_t u0 = cstart[c], u1 = cstart[c + 1];
+        const int64_t K = u1 - u0;                       /* numberOfUsersInCluster :143 */
+        if (K == 0) continue;
+        int any = 0;
+        for (int64_t k = u0; k < u1; k++) any |= wanted[k];
+        if (!any) continue;
+
+        /* items[] = items with >= 1 positive rating from the cluster (:164-174, :238-243), ascending */
+        const int64_t e0 = rowptr[u0], e1 = rowptr[u1];
+        int32_t* items = (int32_t*)malloc(sizeof(int32_t) * (size_t)(e1 - e0 + 1));
+        int32_t* loc = (int32_t*)malloc(sizeof(int32_t) * ((size_t)max_item + 1));
+        if (!items || !loc) { free(items); free(loc); rc = ORC_E_NOMEM; break; }
+        for (int64_t e = e0; e < e1; e++) items[e - e0] = rt[e].item;
+        qsort(items, (size_t)(e1 - e0), sizeof(int32_t), cmp_i32);
+        int64_t I = 0;
+        for (int64_t e = 0; e < e1 - e0; e++)
+            if (e == 0 || items[e] != items[e - 1]) items[I++] = items[e];
+        for (int64_t i = 0; i < I; i++) loc[items[i]] = (int32_t)i;
+
+        /* cache[u][i] = probItemGivenUser(i,u) (:184-190, :384-389) */
+        const int transposed = (p->mode != ORC_MODE_LITERAL);
+        double* P = (double*)malloc(sizeof(double) * (size_t)K * (size_t)I);
+        double* G = NULL;
+        if (!P) { free(items); free(loc); rc = ORC_E_NOMEM; break; }
+#define PAT(v, i) (transposed ? P[(size_t)(i) * (size_t)K + (size_t)(v)] : P[(size_t)(v) * (size_t)I + (size_t)(i)])
+        for (int64_t v = 0; v < K; v++) {
+            const double sum = usum[u0 + v];
+            for (int64_t i = 0; i < I; i++) {
+                const double val = (1 - lambda) * (0.0 / sum) + lambda * iprob[items[i]];
+                if (transposed) P[(size_t)i * (size_t)K + (size_t)v] = val; else P[(size_t)v * (size_t)I + (size_t)i] = val;
+            }
+            for (int64_t e = rowptr[u0 + v]; e < rowptr[u0 + v + 1]; e++) {
+                const int64_t i = loc[rt[e].item];
+                const double rating = (double)rt[e].score;                      /* :173 */
+                const double val = (1 - lambda) * (rating / sum) + lambda * iprob[items[i]]; /* :388 */
+                if (transposed) P[(size_t)i * (size_t)K + (size_t)v] = val; else P[(size_t)v * (size_t)I + (size_t)i] = val;
+            }
+        }
+        if (p->mode == ORC_MODE_GRAM) {
+            G = (double*)malloc(sizeof(double) * (size_t)I * (size_t)I);
+            if (!G) { free(P); free(items); free(loc); rc = ORC_E_NOMEM; break; }
+#pragma omp parallel for schedule(dynamic, 4)
+            for (int64_t i = 0; i < I; i++)
+                for (int64_t j = i; j < I; j++) {
+                    const double* a = P + (size_t)i * (size_t)K;
+                    const double* b = P + (size_t)j * (size_t)K;
+                    double s = 0;
+                    for (int64_t v = 0; v < K; v++) s += a[v] * b[v];
+                    G[(size_t)i * (size_t)I + (size_t)j] = s;
+                    G[(size_t)j * (size_t)I + (size_t)i] = s;
+                }
+        }
+
+        /* per-user result slots so that the parallel loop is deterministic */
+        int64_t* slot = (int64_t*)malloc(sizeof(int64_t) * (size_t)(K + 1));
+        int64_t base = res->count, nslots = 0;
+        for (int64_t v = 0; v < K; v++) {
+            slot[v] = -1;
+            const int64_t n = rowptr[u0 + v + 1] - rowptr[u0 + v];
+            const int64_t cu = I - n;
+            if (!wanted[u0 + v]) continue;
+            if (cu == 0) continue;                        /* :210-213 */
+            if (us[u0 + v].id < p->filter_users) continue; /* :220-223 */
+            slot[v] = base + nslots;
+            nslots += (cu < p->top_n ? cu : p->top_n);
+        }
+        const double log_K = log((double)K);              /* :329 */
+        const double t_begin = now_s();
+        int oom = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int64_t u = 0; u < K; u++) {
+            if (slot[u] < 0) continue;
+            const int64_t r0 = rowptr[u0 + u], r1 = rowptr[u0 + u + 1];
+            const int n = (int)(r1 - r0);
+            const int64_t cu = I - n;
+            cand_t* prefs = (cand_t*)malloc(sizeof(cand_t) * (size_t)cu);
+            char* rated = (char*)calloc((size_t)I, 1);
+            int32_t* rj = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+            if (!prefs || !rated || !rj) { oom = 1; free(prefs); free(rated); free(rj); continue; }
+            for (int k = 0; k < n; k++) { rj[k] = loc[rt[r0 + k].item]; rated[rj[k]] = 1; }
+            const double pvpi = (n - 1) * log_items - n * log_K;               /* :328-329 */
+            int64_t np = 0;
+            for (int64_t i = 0; i < I; i++) {                                   /* :332 */
+                if (rated[i]) continue;
+                double logResult = 0.0;                                        /* :334 */
+                for (int k = 0; k < n; k++) {                                   /* :337 */
+                    const int64_t j = rj[k];
+                    double sum = 0.0;                                          /* :339 */
+                    if (p->mode == ORC_MODE_GRAM) {
+                        sum = G[(size_t)i * (size_t)I + (size_t)j] - PAT(u, i) * PAT(u, j);
+                    } else if (transposed) {
+                        const double* a = P + (size_t)i * (size_t)K;
+                        const double* b = P + (size_t)j * (size_t)K;
+                        for (int64_t v = 0; v < u; v++) sum += a[v] * b[v];
+                        for (int64_t v = u + 1; v < K; v++) sum += a[v] * b[v];
+                    } else {
+                        for (int64_t v = 0; v < K; v++) {                      /* :342-346 */
+                            if (v == u) continue;                              /* neighbours.remove(userID) :216 */
+                            sum += P[(size_t)v * (size_t)I + (size_t)i] * P[(size_t)v * (size_t)I + (size_t)j];
+                        }
+                    }
+                    logResult += log(sum);                                     /* :348 */
+                }
+                logResult += pvpi;                                             /* :352 */
+                prefs[np].score = logResult;
+                prefs[np].item = items[i];
+                np++;
+            }
+            qsort(prefs, (size_t)np, sizeof(cand_t), cmp_cand);
+            const int64_t iterations = np < p->top_n ? np : p->top_n;          /* :360 */
+            for (int64_t k = 0; k < iterations; k++) {                         /* :361-369 */
+                res->user[slot[u] + k] = us[u0 + u].id;
+                res->item[slot[u] + k] = prefs[k].item;
+                res->score[slot[u] + k] = prefs[k].score;
+                res->cluster[slot[u] + k] = c;
+            }
+            free(prefs); free(rated); free(rj);
+        }
+        res->seconds += now_s() - t_begin;
+        for (int64_t v = 0; v < K; v++) if (slot[v] >= 0) res->users_scored++;
+        res->count += nslots;
+        if (oom) rc = ORC_E_NOMEM;
+        free(slot); free(G); free(P); free(items); free(loc);
+#undef PAT
+    }
+
+done:
+    free(us); free(map); free(cstart); free(rt); free(rowptr); free(usum);
+    free(wanted); free(isum); free(iprob);
+    if (rc != ORC_OK) { orc_result_free(res); return rc; }
+    *out = res;
+    return ORC_OK;
+}
+
+int64_t orc_result_count(const orc_result* r) { return r ? r->count : 0; }
+double orc_result_seconds(const orc_result* r) { return r ? r->seconds : 0.0; }
+int64_t orc_result_users_scored(const orc_result* r) { return r ? r->users_scored : 0; }
+
+void orc_result_copy(const orc_result* r, int32_t* user, int32_t* item, double* score64,
+                     float* score32, int32_t* cluster) {
+    if (!r) return;
+    for (int64_t k = 0; k < r->count; k++) {
+        if (user) user[k] = r->user[k];
+        if (item) item[k] = r->item[k];
+        if (score64) score64[k] = r->score[k];
+        if (score32) score32[k] = (float)r->score[k];     /* RM2HDFSReducer.java:48 */
+        if (cluster) cluster[k] = r->cluster[k];
+    }
+}
+
+void orc_result_free(orc_result* r) {
+    if (!r) return;
+    free(r->user); free(r->item); free(r->score); free(r->cluster);
+    free(r);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Config 3: item-item co-occurrence counts on the binarised matrix.  PARITY UNPINNED (Mahout 0.8
+ * RowSimilarityJob/CooccurrenceCountSimilarity, called at
+ * M/baselinerecommender/BaselineRecommenderJob.java:241-253, is not in /root/reference);
+ * semantics restated from Mahout's published definition: C[i][j] = sum_u B[u][i]*B[u][j].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { int32_t user, item; } ui_t;
+static int cmp_ui(const void* a, const void* b) {
+    const ui_t* x = (const ui_t*)a; const ui_t* y = (const ui_t*)b;
+    if (x->user != y->user) return x->user < y->user ? -1 : 1;
+    return x->item < y->item ? -1 : (x->item > y->item ? 1 : 0);
+}
+
+int orc_cooccurrence(const int32_t* r_user, const int32_t* r_item, const float* r_score, int64_t nnz,
+                     int32_t n_user_ids, int32_t n_items, int32_t* C) {
+    if (nnz < 0 || n_items <= 0 || n_user_ids <= 0) return ORC_E_ARG;
+    ui_t* a = (ui_t*)malloc(sizeof(ui_t) * (size_t)(nnz > 0 ? nnz : 1));
+    if (!a) return ORC_E_NOMEM;
+    int64_t m = 0;
+    for (int64_t e = 0; e < nnz; e++) {
+        if (!(r_score[e] > 0)) continue;
+        if (r_item[e] < 0 || r_item[e] >= n_items || r_user[e] < 0 || r_user[e] >= n_user_ids) { free(a); return ORC_E_ARG; }
+        a[m].user = r_user[e]; a[m].item = r_item[e]; m++;
+    }
+    qsort(a, (size_t)m, sizeof(ui_t), cmp_ui);
+    memset(C, 0, sizeof(int32_t) * (size_t)n_items * (size_t)n_items);
+    int64_t s = 0;
+    while (s < m) {
+        int64_t t = s;
+        while (t < m && a[t].user == a[s].user) t++;
+        for (int64_t x = s; x < t; x++) {
+            if (x > s && a[x].item == a[x - 1].item) continue;     /* binarised: duplicates count once */
+            for (int64_t y = s; y < t; y++) {
+                if (y > s && a[y].item == a[y - 1].item) continue;
+                C[(size_t)a[x].item * (size_t)n_items + (size_t)a[y].item] += 1;
+            }
+        }
+        s = t;
+    }
+    free(a);
+    return ORC_OK;
+}

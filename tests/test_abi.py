@@ -1,0 +1,55 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/filmyou_rm2.h declares
+(no compute calls without a GPU), and fails loudly when no device is present."""
+import os
+import re
+
+import pytest
+
+import filmyou_core_b200 as fy
+from filmyou_core_b200 import engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "filmyou_rm2.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fy_(?:rm2|cooc)_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_and_binding_list_the_same_symbols():
+    assert _declared() == sorted(engine.EXPORTS)
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    fy.build_library()
+    L = fy.load_library()
+    for name in _declared():
+        assert hasattr(L, name), name
+    assert L.fy_rm2_abi_version() == 1
+
+
+def test_default_params_match_the_reference_defaults():
+    L = fy.load_library()
+    p = fy.Rm2Params()
+    L.fy_rm2_default_params(p)
+    # M/rmrecommender/RMRecommenderDriver.java:95,114,119
+    assert (p.lambda_, p.top_n, p.filter_users, p.shard_count) == (0.1, 1000, 0, 1)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(fy.Rm2Error) as e:
+        fy.Rm2Engine(number_of_items=10)
+    assert e.value.code == -7
+
+
+def test_product_package_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "filmyou_core_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(d, f)).read()
+                assert "oracle" not in txt.lower() or f == "__init__.py" and False, os.path.join(d, f)
