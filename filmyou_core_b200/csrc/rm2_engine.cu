@@ -647,6 +647,18 @@ extern "C" int fy_rm2_results(fy_rm2_ctx* ctx, int32_t* user, int32_t* item, dou
     });
 }
 
+extern "C" int fy_rm2_results_device(fy_rm2_ctx* ctx, const int32_t** user, const int32_t** item, const double** score64,
+                                     const float** score32, const int32_t** cluster) {
+    if (!ctx) return FY_E_ARG;
+    if (!ctx->have_results) return ctx->fail(FY_E_STATE, "fy_rm2_results_device needs a successful fy_rm2_run");
+    if (user) *user = ctx->p_user.p;
+    if (item) *item = ctx->p_item.p;
+    if (score64) *score64 = ctx->p_s64.p;
+    if (score32) *score32 = ctx->p_s32.p;
+    if (cluster) *cluster = ctx->p_cluster.p;
+    return FY_OK;
+}
+
 extern "C" int fy_rm2_get_profile(const fy_rm2_ctx* ctx, fy_rm2_profile* out) {
     if (!ctx || !out) return FY_E_ARG;
     *out = ctx->prof;

@@ -25,7 +25,7 @@ STATUS = {
 EXPORTS = [
     "fy_rm2_abi_version", "fy_rm2_default_params", "fy_rm2_create", "fy_rm2_destroy", "fy_rm2_last_error",
     "fy_rm2_set_stream", "fy_rm2_set_ratings", "fy_rm2_set_clustering", "fy_rm2_run", "fy_rm2_max_item",
-    "fy_rm2_stats", "fy_rm2_result_count", "fy_rm2_users_scored", "fy_rm2_results", "fy_rm2_score_group",
+    "fy_rm2_stats", "fy_rm2_result_count", "fy_rm2_users_scored", "fy_rm2_results", "fy_rm2_results_device", "fy_rm2_score_group",
     "fy_rm2_get_profile", "fy_cooc_counts", "fy_cooc_topk",
 ]
 
@@ -106,6 +106,7 @@ def load_library():
     L.fy_rm2_users_scored.argtypes = [vp]
     L.fy_rm2_users_scored.restype = C.c_int64
     L.fy_rm2_results.argtypes = [vp, i32p, i32p, f64p, f32p, i32p]
+    L.fy_rm2_results_device.argtypes = [vp] + [C.POINTER(vp)] * 5
     L.fy_rm2_score_group.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, i32p, f64p, C.c_int32,
                                      i32p, i32p, f32p, C.c_int64, f64p, C.c_int32]
     L.fy_rm2_get_profile.argtypes = [vp, C.POINTER(Rm2Profile)]
@@ -123,6 +124,12 @@ def _ptr(a, t):
 
 def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class _DeviceArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2,
+                                         "strides": None}
 
 
 class Rm2Engine:
@@ -210,6 +217,15 @@ class Rm2Engine:
                                             _ptr(out["score64"], C.c_double), _ptr(out["score32"], C.c_float),
                                             _ptr(out["cluster"], C.c_int32)))
         return {k: v[:n] for k, v in out.items()}
+
+    def results_device(self):
+        """field -> object exposing __cuda_array_interface__ over the device-resident packed arrays
+        (zero copy; wrap with torch.as_tensor(x, device="cuda")).  Valid until the next run()."""
+        n = self.result_count()
+        ptrs = [C.c_void_p() for _ in range(5)]
+        self._check(self._L.fy_rm2_results_device(self._h, *[C.byref(p) for p in ptrs]))
+        spec = (("user", "<i4"), ("item", "<i4"), ("score64", "<f8"), ("score32", "<f4"), ("cluster", "<i4"))
+        return {name: _DeviceArray(p.value or 0, n, ts) for (name, ts), p in zip(spec, ptrs)}
 
     def score_group(self, cluster_id, split, n_splits, group_user, group_user_sum, r_user, r_item, r_score, item_prob):
         group_user, r_user, r_item = _i32(group_user), _i32(r_user), _i32(r_item)

@@ -113,6 +113,11 @@ int64_t fy_rm2_users_scored(const fy_rm2_ctx* ctx);
 int fy_rm2_results(fy_rm2_ctx* ctx, int32_t* user, int32_t* item, double* score64, float* score32,
                    int32_t* cluster);
 
+/* Device-resident view of the same packed arrays (valid until the next run / destroy), so that a
+ * multi-GPU host can hand them to NCCL without a host round trip.  Any output pointer may be NULL. */
+int fy_rm2_results_device(fy_rm2_ctx* ctx, const int32_t** user, const int32_t** item, const double** score64,
+                          const float** score32, const int32_t** cluster);
+
 /* Fine seam: one reduce() group, exactly the records the reducer receives
  * (M/rm/AbstractRM2Reducer.java:149-174): n_group_users (user, userSum) records, then the group's
  * rating records; item_prob is rm2/itemColl indexed by item id (size max_item+1).
