@@ -83,18 +83,23 @@ struct fy_rm2_ctx {
     DBuf<float> s_score;
     DBuf<int32_t> src_a, csc_src, rowptr;
     DBuf<unsigned char> cub_tmp;
-    DBuf<double> usum, isum, iprob, bvec, total, work, work_scan;
+    DBuf<double> usum, isum, iprob, bvec, total, work, work_scan, tsum;
+    DBuf<unsigned long long> ustat[2];
+    bool exact_scores = false;
     DBuf<unsigned long long> counters;   // [0] n_valid, [1] truncated counter, [2] bits of the smallest positive b_i
     DBuf<int> flags, imax;
     DBuf<int32_t> ifirst, ilast, tstart, tend, tloc, icount, item_off;
-    DBuf<int32_t> c_item, c_start, c_len, csr_loc, csc_lu, chunk_ptr;
+    DBuf<int32_t> c_item, c_start, c_len, csr_loc, csc_lu;
     DBuf<double> c_b, c_alpha, csr_delta, csc_delta, csr_c;
     int32_t m = 0;
     std::vector<int32_t> h_icount, h_item_off;
     double h_total = 0.0;
 
     // ---- per cluster ----
-    DBuf<double> H, scores;
+    DBuf<double> H[2], scores[2];
+    DBuf<int32_t> chunk_ptr2[2];
+    cudaStream_t stream_g = nullptr, stream_t = nullptr;   // H build / top-N run beside the score stream
+    cudaEvent_t sync_ev[10] = {nullptr};
 
     // ---- results ----
     int32_t shard_begin = 0, shard_end = 0, out_stride = 0;
@@ -126,6 +131,13 @@ struct fy_rm2_ctx {
 #define LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
     do {                                                                              \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);              \
+        (ctx)->launches++;                                                            \
+        CK(cudaGetLastError());                                                       \
+    } while (0)
+
+#define LAUNCH_ON(ctx, strm, kernel, grid, block, smem, ...)                          \
+    do {                                                                              \
+        kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                     \
         (ctx)->launches++;                                                            \
         CK(cudaGetLastError());                                                       \
     } while (0)
@@ -195,6 +207,9 @@ extern "C" void fy_rm2_destroy(fy_rm2_ctx* ctx) {
     cudaSetDevice(ctx->prm.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->sync_ev) if (e) cudaEventDestroy(e);
+    if (ctx->stream_g) { cudaStreamSynchronize(ctx->stream_g); cudaStreamDestroy(ctx->stream_g); }
+    if (ctx->stream_t) { cudaStreamSynchronize(ctx->stream_t); cudaStreamDestroy(ctx->stream_t); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -243,6 +258,7 @@ static int upload_ratings(fy_rm2_ctx* ctx, const int32_t* user, const int32_t* i
     if (rc != FY_OK) return rc;
     if (h_max < 0) return ctx->fail(FY_E_ARG, "no rating with score > 0");
     ctx->nnz = nnz;
+    ctx->exact_scores = (h_flags[fy::DF_INEXACT_SCORES] == 0);
     ctx->max_item = h_max;
     ctx->have_ratings = true;
     return FY_OK;
@@ -321,10 +337,11 @@ extern "C" int fy_rm2_set_clustering(fy_rm2_ctx* ctx, const int32_t* user, const
 // the pipeline
 // ---------------------------------------------------------------------------------------------
 template <int L>
-static void launch_score(fy_rm2_ctx* ctx, dim3 grid, const double* H, int32_t I_c, int32_t ld, int32_t rank_begin,
-                         int32_t slot0, double log_items, double log_K) {
-    LAUNCH(ctx, fy::k_score<L>, grid, fy::SCORE_THREADS, 0, H, I_c, ld, rank_begin, slot0, ctx->rowptr.p,
-           ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, log_items, log_K, ctx->scores.p);
+static void launch_score(fy_rm2_ctx* ctx, cudaStream_t strm, dim3 grid, const double* H, int32_t I_c, int32_t ld,
+                         int32_t rank_begin, int32_t slot0, double log_items, double log_K, double* scores,
+                         unsigned long long* ustat) {
+    LAUNCH_ON(ctx, strm, fy::k_score<L>, grid, fy::SCORE_THREADS, 0, H, I_c, ld, rank_begin, slot0, ctx->rowptr.p,
+              ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, log_items, log_K, scores, ustat);
 }
 
 static int run_pipeline(fy_rm2_ctx* ctx) {
@@ -401,9 +418,16 @@ static int run_pipeline(fy_rm2_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->tstart.p, 0xff, tab * 4, st));
     LAUNCH(ctx, k_item_groups, cdiv(m, 256), 256, 0, keys2, m, rank_bits, ctx->rank_cluster.p, TI,
            ctx->ifirst.p, ctx->ilast.p, ctx->tstart.p, ctx->tend.p);
-    LAUNCH(ctx, k_item_prob, cdiv(TI, 128), 128, 0, ctx->ifirst.p, ctx->ilast.p, ctx->csc_src.p, ctx->s_score.p, TI,
-           ctx->counters.p + 1, ctx->use_ext ? ctx->ext_iprob.p : (const double*)nullptr, lambda,
-           ctx->isum.p, ctx->iprob.p, ctx->bvec.p, ctx->total.p, ctx->counters.p + 2);
+    if (ctx->exact_scores && !ctx->use_ext) {
+        ctx->tsum.need(tab);
+        LAUNCH(ctx, k_group_sum, cdiv((int64_t)tab, 256), 256, 0, ctx->tstart.p, ctx->tend.p, ctx->csc_src.p, ctx->s_score.p, tab, ctx->tsum.p);
+        LAUNCH(ctx, k_item_prob_fast, cdiv(TI, 128), 128, 0, ctx->tsum.p, KC, TI, ctx->counters.p + 1, lambda,
+               ctx->isum.p, ctx->iprob.p, ctx->bvec.p, ctx->total.p, ctx->counters.p + 2);
+    } else {
+        LAUNCH(ctx, k_item_prob, cdiv(TI, 128), 128, 0, ctx->ifirst.p, ctx->ilast.p, ctx->csc_src.p, ctx->s_score.p, TI,
+               ctx->counters.p + 1, ctx->use_ext ? ctx->ext_iprob.p : (const double*)nullptr, lambda,
+               ctx->isum.p, ctx->iprob.p, ctx->bvec.p, ctx->total.p, ctx->counters.p + 2);
+    }
     LAUNCH(ctx, k_cluster_item_count, KC, 256, 0, ctx->tstart.p, TI, ctx->icount.p);
     LAUNCH(ctx, k_cluster_offsets, 1, 32, 0, ctx->icount.p, KC, ctx->item_off.p);
 
@@ -459,9 +483,8 @@ static int run_pipeline(fy_rm2_ctx* ctx) {
            ctx->bvec.p, ctx->tloc.p, TI, lambda, ctx->csr_loc.p, ctx->csr_delta.p);
     LAUNCH(ctx, k_csc_fill, cdiv(m, 256), 256, 0, keys2, ctx->csc_src.p, m, rank_bits, ctx->rank_cluster.p, ctx->cstart.p,
            ctx->csr_delta.p, ctx->csc_lu.p, ctx->csc_delta.p);
-    LAUNCH(ctx, k_alpha, cdiv(n_slots, 128), 128, 0, ctx->c_start.p, ctx->c_len.p, ctx->csc_delta.p, n_slots, ctx->c_alpha.p);
-    LAUNCH(ctx, k_cuj, cdiv(m, 128), 128, 0, keys, m, item_bits, ctx->rank_cluster.p, ctx->cstart.p, ctx->item_off.p,
-           ctx->csr_loc.p, ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, ctx->csc_src.p, ctx->csc_delta.p, ctx->csr_c.p);
+    LAUNCH(ctx, k_alpha_cuj, cdiv(n_slots, 128), 128, 0, ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, keys2, rank_bits,
+           ctx->rank_cluster.p, ctx->cstart.p, ctx->csc_src.p, ctx->csc_delta.p, n_slots, ctx->c_alpha.p, ctx->csr_c.p);
     CK(cudaEventRecord(ev_index, st));
 
     // ---------------- exponent-peel period L from a lower bound on t ----------------
@@ -494,58 +517,128 @@ static int run_pipeline(fy_rm2_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->out_count.p, 0, ((size_t)std::max(n_rows, 1) + 1) * 4, st));
     const double log_items = std::log((double)ctx->prm.number_of_items);   // AbstractRM2Reducer.java:328
 
-    // timeline: every mark opens a segment of the given kind; elapsed time goes to that kind
-    enum { SEG_GRAM = 0, SEG_SCORE = 1, SEG_TOPN = 2, SEG_END = 3 };
-    std::vector<std::pair<int, size_t>> marks;
-    auto mark = [&](int kind) { CK(cudaEventRecord(ctx->ev(evi), st)); marks.emplace_back(kind, evi); evi++; };
+    // Three streams: H build of cluster c+1 (latency / DRAM-write bound) and top-N of cluster c-1 run
+    // beside the score kernel of cluster c (L1/L2-fabric bound); H and the score matrix are double
+    // buffered.  Each stage is timed with events on its own stream.
+    // (Stream priorities were tried: measured no gain -- the run sits at the 1 kW power cap, so the
+    //  stages do not hide each other; the side streams only fill launch gaps and tails, ~2 %.)
+    if (!ctx->stream_g) CK(cudaStreamCreateWithFlags(&ctx->stream_g, cudaStreamNonBlocking));
+    if (!ctx->stream_t) CK(cudaStreamCreateWithFlags(&ctx->stream_t, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : ctx->sync_ev) if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaStream_t sS = st, sG = ctx->stream_g, sT = ctx->stream_t;
+    cudaEvent_t* hReady = ctx->sync_ev;       // [2] H[b] built
+    cudaEvent_t* hFree = ctx->sync_ev + 2;    // [2] last score kernel reading H[b] finished
+    cudaEvent_t* sReady = ctx->sync_ev + 4;   // [2] scores[b] written
+    cudaEvent_t* sFree = ctx->sync_ev + 6;    // [2] top-N finished reading scores[b]
+    cudaEvent_t evFork = ctx->sync_ev[8], evJoin = ctx->sync_ev[9];
+    CK(cudaEventRecord(evFork, st));
+    CK(cudaStreamWaitEvent(sG, evFork, 0));
+    CK(cudaStreamWaitEvent(sT, evFork, 0));
+    enum { SEG_GRAM = 0, SEG_SCORE = 1, SEG_TOPN = 2 };
+    struct Seg { int kind; size_t e0, e1; };
+    std::vector<Seg> segs;
+    auto seg_begin = [&](int kind, cudaStream_t strm) { CK(cudaEventRecord(ctx->ev(evi), strm)); segs.push_back(Seg{kind, evi, 0}); evi++; return segs.size() - 1; };
+    auto seg_end = [&](size_t k, cudaStream_t strm) { CK(cudaEventRecord(ctx->ev(evi), strm)); segs[k].e1 = evi; evi++; };
     const size_t SCORE_BUF_BYTES = (size_t)2 << 30;
+    auto h_geometry = [&](int32_t I_c, int32_t& ld, int32_t& slice_w, int32_t& chunk_w, int32_t& nchunk, int32_t& n_bound) {
+        ld = cdiv(I_c, SCORE_TILE) * SCORE_TILE;
+        nchunk = cdiv(I_c, H_MAX_CHUNK);
+        slice_w = cdiv(cdiv(cdiv(I_c, nchunk), H_WARPS), 8) * 8;
+        chunk_w = slice_w * H_WARPS;
+        nchunk = cdiv(I_c, chunk_w);
+        n_bound = nchunk * H_WARPS + 1;
+    };
+    {   // size the per-cluster buffers once (growing them inside the loop would synchronise the device)
+        size_t need_h = 0, need_cp = 0, need_sc = 0, need_us = 0;
+        int n_touched = 0, n_batches = 0;
+        for (int32_t c = 0; c < KC; c++) {
+            const int32_t cs = ctx->h_cstart[c], ce = ctx->h_cstart[c + 1];
+            const int32_t r0 = std::max(cs, ub), r1 = std::min(ce, ue), I_c = ctx->h_icount[c];
+            if (r1 <= r0 || I_c <= 0) continue;
+            int32_t ld, slice_w, chunk_w, nchunk, n_bound;
+            h_geometry(I_c, ld, slice_w, chunk_w, nchunk, n_bound);
+            const size_t batch = std::max<size_t>(1, std::min<size_t>((size_t)(r1 - r0), SCORE_BUF_BYTES / ((size_t)ld * 8)));
+            need_h = std::max(need_h, (size_t)I_c * ld);
+            need_cp = std::max(need_cp, (size_t)(ce - cs) * n_bound);
+            need_sc = std::max(need_sc, batch * ld);
+            need_us = std::max(need_us, batch * 3);
+            n_touched++; n_batches += cdiv(r1 - r0, (int64_t)batch);
+        }
+        for (int b = 0; b < 2; b++) {
+            if (b == 1 && n_touched < 2) need_h = need_cp = 0;     // a single cluster needs one H
+            if (b == 1 && n_batches < 2) need_sc = need_us = 0;
+            ctx->H[b].need(need_h); ctx->chunk_ptr2[b].need(need_cp); ctx->scores[b].need(need_sc); ctx->ustat[b].need(need_us);
+        }
+    }
+    int hb = 0, sb = 0;
+    bool h_used[2] = {false, false}, s_used[2] = {false, false};
     for (int32_t c = 0; c < KC; c++) {
         const int32_t cs = ctx->h_cstart[c], ce = ctx->h_cstart[c + 1];
         const int32_t r0 = std::max(cs, ub), r1 = std::min(ce, ue);
         if (r1 <= r0) continue;
         const int32_t K_c = ce - cs, I_c = ctx->h_icount[c], slot0 = ctx->h_item_off[c];
         if (I_c <= 0) continue;
-        const int32_t ld = cdiv(I_c, SCORE_TILE) * SCORE_TILE;
-        const int32_t nchunk = cdiv(I_c, H_MAX_CHUNK);
-        const int32_t chunk_w = cdiv(cdiv(I_c, nchunk), 32) * 32;
+        int32_t ld, slice_w, chunk_w, nchunk, n_bound;
+        h_geometry(I_c, ld, slice_w, chunk_w, nchunk, n_bound);
         ctx->prof.gram_bytes += (double)I_c * ld * 8.0;
-        ctx->H.need((size_t)I_c * ld);
-        ctx->chunk_ptr.need((size_t)K_c * (nchunk + 1));
-        mark(SEG_GRAM);
-        LAUNCH(ctx, k_chunk_ptr, cdiv((int64_t)K_c * (nchunk + 1), 256), 256, 0, cs, K_c, nchunk, chunk_w,
-               ctx->rowptr.p, ctx->csr_loc.p, ctx->chunk_ptr.p);
+        // ---- stream G: H[hb] ----
+        if (h_used[hb]) CK(cudaStreamWaitEvent(sG, hFree[hb], 0));
         {
+            const size_t k = seg_begin(SEG_GRAM, sG);
+            LAUNCH_ON(ctx, sG, k_chunk_ptr, cdiv((int64_t)K_c * n_bound, 256), 256, 0, cs, K_c, n_bound, slice_w,
+                      ctx->rowptr.p, ctx->csr_loc.p, ctx->chunk_ptr2[hb].p);
             const size_t smem = (size_t)chunk_w * sizeof(double);
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_build_H, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LAUNCH(ctx, k_build_H, dim3(I_c, nchunk), H_THREADS, smem, I_c, ld, chunk_w, nchunk, slot0,
-                   ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, ctx->c_alpha.p, ctx->csc_lu.p, ctx->csc_delta.p,
-                   ctx->chunk_ptr.p, ctx->csr_loc.p, ctx->csr_delta.p, ctx->H.p);
+            if (smem > 24 * 1024) CK(cudaFuncSetAttribute(k_build_H, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LAUNCH_ON(ctx, sG, k_build_H, dim3(I_c, nchunk), H_THREADS, smem, I_c, ld, slice_w, n_bound, slot0,
+                      ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, ctx->c_alpha.p, ctx->csc_lu.p, ctx->csc_delta.p,
+                      ctx->chunk_ptr2[hb].p, ctx->csr_loc.p, ctx->csr_delta.p, ctx->H[hb].p);
+            seg_end(k, sG);
         }
+        CK(cudaEventRecord(hReady[hb], sG));
+        h_used[hb] = true;
+        // ---- stream S: scores; stream T: top-N ----
+        CK(cudaStreamWaitEvent(sS, hReady[hb], 0));
         const double log_K = std::log((double)K_c);                        // :329
         const int32_t batch = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)(r1 - r0), SCORE_BUF_BYTES / ((size_t)ld * 8)));
-        ctx->scores.need((size_t)batch * ld);
         int P2 = 1; while (P2 < std::min(ctx->prm.top_n, I_c)) P2 <<= 1;
         const size_t topn_smem = (size_t)P2 * 12;
-        if (topn_smem > 40 * 1024) CK(cudaFuncSetAttribute(k_topn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topn_smem));
+        if (topn_smem > 36 * 1024) CK(cudaFuncSetAttribute(k_topn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topn_smem));
         for (int32_t b0 = r0; b0 < r1; b0 += batch) {
             const int32_t nb = std::min(batch, r1 - b0);
             const dim3 grid(nb, ld / SCORE_TILE);
-            mark(SEG_SCORE);
-            switch (L) {
-                case 8: launch_score<8>(ctx, grid, ctx->H.p, I_c, ld, b0, slot0, log_items, log_K); break;
-                case 4: launch_score<4>(ctx, grid, ctx->H.p, I_c, ld, b0, slot0, log_items, log_K); break;
-                case 2: launch_score<2>(ctx, grid, ctx->H.p, I_c, ld, b0, slot0, log_items, log_K); break;
-                default: launch_score<1>(ctx, grid, ctx->H.p, I_c, ld, b0, slot0, log_items, log_K); break;
+            if (s_used[sb]) CK(cudaStreamWaitEvent(sS, sFree[sb], 0));
+            LAUNCH_ON(ctx, sS, k_init_ustat, cdiv(nb, 256), 256, 0, ctx->ustat[sb].p, nb);
+            {
+                const size_t k = seg_begin(SEG_SCORE, sS);
+                switch (L) {
+                    case 8: launch_score<8>(ctx, sS, grid, ctx->H[hb].p, I_c, ld, b0, slot0, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
+                    case 4: launch_score<4>(ctx, sS, grid, ctx->H[hb].p, I_c, ld, b0, slot0, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
+                    case 2: launch_score<2>(ctx, sS, grid, ctx->H[hb].p, I_c, ld, b0, slot0, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
+                    default: launch_score<1>(ctx, sS, grid, ctx->H[hb].p, I_c, ld, b0, slot0, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
+                }
+                seg_end(k, sS);
             }
             ctx->prof.score_launches++;
-            mark(SEG_TOPN);
-            LAUNCH(ctx, k_topn, nb, TOPN_THREADS, topn_smem, ctx->scores.p, I_c, ld, b0, slot0, ctx->prm.top_n, out_stride,
-                   ctx->prm.filter_users, ctx->split, ctx->n_splits, ctx->rank_userid.p, ctx->c_item.p,
-                   b0 - ub, ctx->out_item.p, ctx->out_score.p, ctx->out_count.p);
+            CK(cudaEventRecord(sReady[sb], sS));
+            s_used[sb] = true;
+            CK(cudaStreamWaitEvent(sT, sReady[sb], 0));
+            {
+                const size_t k = seg_begin(SEG_TOPN, sT);
+                LAUNCH_ON(ctx, sT, k_topn, nb, TOPN_THREADS, topn_smem, ctx->scores[sb].p, ctx->ustat[sb].p, I_c, ld, b0, slot0,
+                          ctx->prm.top_n, out_stride, ctx->prm.filter_users, ctx->split, ctx->n_splits, ctx->rank_userid.p,
+                          ctx->c_item.p, b0 - ub, ctx->out_item.p, ctx->out_score.p, ctx->out_count.p);
+                seg_end(k, sT);
+            }
+            CK(cudaEventRecord(sFree[sb], sT));
+            if (ctx->scores[1].cap) sb ^= 1;
         }
+        CK(cudaEventRecord(hFree[hb], sS));
+        if (ctx->H[1].cap) hb ^= 1;
         ctx->prof.clusters_touched++;
     }
-    mark(SEG_END);
+    // join
+    CK(cudaEventRecord(evJoin, sG)); CK(cudaStreamWaitEvent(st, evJoin, 0));
+    CK(cudaEventRecord(evFork, sT)); CK(cudaStreamWaitEvent(st, evFork, 0));
 
     // ---------------- pack ----------------
     if (n_rows > 0) {
@@ -584,11 +677,11 @@ static int run_pipeline(fy_rm2_ctx* ctx) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ev_start, ev_end)); ctx->prof.ms_total = ms;
     CK(cudaEventElapsedTime(&ms, ev_start, ev_index)); ctx->prof.ms_index = ms;
-    for (size_t k = 0; k + 1 < marks.size(); k++) {
-        CK(cudaEventElapsedTime(&ms, ctx->ev(marks[k].second), ctx->ev(marks[k + 1].second)));
-        if (marks[k].first == SEG_GRAM) ctx->prof.ms_gram += ms;
-        else if (marks[k].first == SEG_SCORE) ctx->prof.ms_score += ms;
-        else if (marks[k].first == SEG_TOPN) ctx->prof.ms_topn += ms;
+    for (const Seg& g : segs) {
+        CK(cudaEventElapsedTime(&ms, ctx->ev(g.e0), ctx->ev(g.e1)));
+        if (g.kind == SEG_GRAM) ctx->prof.ms_gram += ms;
+        else if (g.kind == SEG_SCORE) ctx->prof.ms_score += ms;
+        else if (g.kind == SEG_TOPN) ctx->prof.ms_topn += ms;
     }
     ctx->prof.log_terms = terms;
     ctx->prof.score_bytes = 8.0 * terms;

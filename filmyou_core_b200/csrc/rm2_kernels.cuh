@@ -28,14 +28,17 @@ enum DevFlag : int {
     DF_DUPLICATE = 1,
     DF_USER_WITHOUT_RATING = 2,
     DF_BAD_ITEM = 3,
+    DF_INEXACT_SCORES = 4,   // informational: some score is not a multiple of 2^-16 below 2^15
     DF_COUNT = 8
 };
 
 constexpr int SCORE_TILE = 256;     // candidates per score CTA (2 per thread)
 constexpr int SCORE_THREADS = 128;
 constexpr int SCORE_CHUNK = 512;    // rated items staged in shared memory at a time
-constexpr int H_MAX_CHUNK = 8192;   // columns of one H row accumulated per CTA (64 KB of doubles)
-constexpr int H_THREADS = 256;
+constexpr int H_MAX_CHUNK = 12288;  // columns of one H row accumulated per CTA (<= 96 KB of doubles)
+constexpr int H_THREADS = 512;
+constexpr int H_WARPS = H_THREADS / 32;   // each warp owns one contiguous column slice of the chunk
+constexpr int H_RB = 128;           // raters staged per batch
 constexpr int TOPN_THREADS = 512;
 constexpr int TOPN_MAX_SELECT = 4096;
 
@@ -88,6 +91,10 @@ __global__ void k_scan_ratings(const int32_t* __restrict__ r_item, const float* 
     if (e < nnz && r_score[e] > 0.0f) {
         local_max = r_item[e];
         if (local_max < 0) { atomicOr(&flags[DF_BAD_ITEM], 1); local_max = -1; }
+        // sums of such scores are exact in double in ANY order (up to 2^22 addends), which lets the
+        // item sums be reduced in parallel and still equal the reference's sequential double sum
+        const float sc = r_score[e] * 65536.0f;
+        if (!(r_score[e] < 32768.0f) || sc != truncf(sc)) atomicOr(&flags[DF_INEXACT_SCORES], 1);
     }
     for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
     if ((threadIdx.x & 31) == 0 && local_max >= 0) atomicMax(max_item, local_max);
@@ -184,6 +191,39 @@ __global__ void k_item_prob(const int32_t* __restrict__ ifirst, const int32_t* _
     bvec[i] = b;
     // smallest b over rated items (positive doubles order like their bit patterns); 0 if any b is 0
     if (x1 > x0) atomicMin(bmin_bits, (unsigned long long)__double_as_longlong(b > 0.0 ? b : 0.0));
+}
+
+// fast path of RM2-2 when every score is a small dyadic rational (DF_INEXACT_SCORES clear): the
+// double sums are exact, so partial sums per (cluster, item) group combined per item give the same
+// bits as the sequential sum above.
+__global__ void k_group_sum(const int32_t* __restrict__ tstart, const int32_t* __restrict__ tend,
+                            const int32_t* __restrict__ csc_src, const float* __restrict__ s_score,
+                            size_t n_cells, double* __restrict__ tsum) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_cells) return;
+    const int32_t x0 = tstart[t];
+    double s = 0.0;
+    if (x0 >= 0) {
+        const int32_t x1 = tend[t];
+        for (int32_t x = x0; x < x1; x++) s += (double)s_score[csc_src[x]];
+    }
+    tsum[t] = s;
+}
+
+__global__ void k_item_prob_fast(const double* __restrict__ tsum, int32_t n_clusters, int32_t table_items,
+                                 const unsigned long long* __restrict__ counter, double lambda,
+                                 double* __restrict__ isum, double* __restrict__ iprob, double* __restrict__ bvec,
+                                 double* __restrict__ total_out, unsigned long long* __restrict__ bmin_bits) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double total = __ddiv_rn((double)(long long)(*counter), 100.0);   // RM2Job.java:95
+    if (i == 0) *total_out = total;
+    if (i >= table_items) return;
+    double s = 0.0;
+    for (int32_t c = 0; c < n_clusters; c++) s += tsum[(size_t)c * table_items + i];
+    const double p = (s > 0.0) ? __ddiv_rn(s, total) : 0.0;
+    const double b = __dmul_rn(lambda, p);
+    isum[i] = s; iprob[i] = p; bvec[i] = b;
+    if (s > 0.0) atomicMin(bmin_bits, (unsigned long long)__double_as_longlong(b > 0.0 ? b : 0.0));
 }
 
 // number of distinct items of each cluster
@@ -288,37 +328,31 @@ __global__ void k_csc_fill(const uint64_t* __restrict__ keys2, const int32_t* __
     csc_delta[x] = csr_delta[csc_src[x]];
 }
 
-// alpha per (cluster, local item): sum of d over the raters, ascending user
-__global__ void k_alpha(const int32_t* __restrict__ c_start, const int32_t* __restrict__ c_len,
-                        const double* __restrict__ csc_delta, int32_t n_slots, double* __restrict__ c_alpha) {
+// alpha_j = sum of d over the raters of j (ascending user), and for every rater u of j
+//   c(u,j) = (K-1)*b_j + sum_{v != u, v rated j} d_vj = (K-1)*b_j + (prefix before u + suffix after u)
+// one thread per (cluster, item) slot; all terms non-negative, so no cancellation for any lambda.
+__global__ void k_alpha_cuj(const int32_t* __restrict__ c_start, const int32_t* __restrict__ c_len,
+                            const double* __restrict__ c_b, const uint64_t* __restrict__ keys2, int rank_bits,
+                            const int32_t* __restrict__ rank_cluster, const int32_t* __restrict__ cstart,
+                            const int32_t* __restrict__ csc_src, const double* __restrict__ csc_delta,
+                            int32_t n_slots, double* __restrict__ c_alpha, double* __restrict__ csr_c) {
     const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_slots) return;
     const int32_t x0 = c_start[s], n = c_len[s];
-    double a = 0.0;
-    for (int32_t r = 0; r < n; r++) a = __dadd_rn(a, csc_delta[x0 + r]);
-    c_alpha[s] = a;
-}
-
-// c(u,j) = (K-1)*b_j + sum_{v != u, v rated j} d_vj   for every CSR entry (u,j)
-__global__ void k_cuj(const uint64_t* __restrict__ keys, int32_t m, int item_bits,
-                      const int32_t* __restrict__ rank_cluster, const int32_t* __restrict__ cstart,
-                      const int32_t* __restrict__ item_off, const int32_t* __restrict__ csr_loc,
-                      const int32_t* __restrict__ c_start, const int32_t* __restrict__ c_len,
-                      const double* __restrict__ c_b, const int32_t* __restrict__ csc_src,
-                      const double* __restrict__ csc_delta, double* __restrict__ csr_c) {
-    const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= m) return;
-    const int32_t rank = (int32_t)(keys[e] >> item_bits);
-    const int32_t c = rank_cluster[rank];
-    const int32_t K = cstart[c + 1] - cstart[c];
-    const int32_t slot = item_off[c] + csr_loc[e];
-    const int32_t x0 = c_start[slot], n = c_len[slot];
-    double a = 0.0;
+    const int32_t c = rank_cluster[(int32_t)(keys2[x0] & ((1ull << rank_bits) - 1))];
+    const double km1b = __dmul_rn((double)(cstart[c + 1] - cstart[c] - 1), c_b[s]);
+    double pre = 0.0;
     for (int32_t r = 0; r < n; r++) {
-        const int32_t x = x0 + r;
-        if (csc_src[x] != e) a = __dadd_rn(a, csc_delta[x]);
+        csr_c[csc_src[x0 + r]] = pre;
+        pre = __dadd_rn(pre, csc_delta[x0 + r]);
     }
-    csr_c[e] = __dadd_rn(__dmul_rn((double)(K - 1), c_b[slot]), a);
+    c_alpha[s] = pre;
+    double suf = 0.0;
+    for (int32_t r = n - 1; r >= 0; r--) {
+        const int32_t e = csc_src[x0 + r];
+        csr_c[e] = __dadd_rn(km1b, __dadd_rn(csr_c[e], suf));
+        suf = __dadd_rn(suf, csc_delta[x0 + r]);
+    }
 }
 
 // per-user work estimate n_u * I_c (for sharding) as double
@@ -336,57 +370,103 @@ __global__ void k_user_work(const int32_t* __restrict__ rowptr, const int32_t* _
 // every bit of H -- is fixed, and two identical item columns give identical H columns (exact ties
 // stay exact ties, as in the reference's double loop).
 // ---------------------------------------------------------------------------------------------
-// first CSR entry of every (user, column chunk) of one cluster: removes the per-rater binary
-// searches from k_build_H
-__global__ void k_chunk_ptr(int32_t rank0, int32_t K_c, int32_t nchunk, int32_t chunk_w,
+// first CSR entry of every (user, column slice) of one cluster; slice q covers local item ids
+// [q*slice_w, (q+1)*slice_w); n_bound = number of slices + 1
+__global__ void k_chunk_ptr(int32_t rank0, int32_t K_c, int32_t n_bound, int32_t slice_w,
                             const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_loc,
                             int32_t* __restrict__ chunk_ptr) {
     const int32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= K_c * (nchunk + 1)) return;
-    const int32_t u = idx / (nchunk + 1), q = idx % (nchunk + 1);
+    if (idx >= K_c * n_bound) return;
+    const int32_t u = idx / n_bound, q = idx % n_bound;
     int32_t a = rowptr[rank0 + u], b = rowptr[rank0 + u + 1];
-    const int32_t target = q * chunk_w;
+    const int32_t target = q * slice_w;
     while (a < b) { const int32_t mid = (a + b) >> 1; if (csr_loc[mid] < target) a = mid + 1; else b = mid; }
     chunk_ptr[idx] = a;
 }
 
+// CTA = (row j, column chunk of H_WARPS slices).  Warp w owns slice w of the chunk: it walks the
+// flattened list of (rater of j, that rater's entries inside the slice) 32 at a time, so lanes stay
+// busy however few entries one rater has in the slice, and no block barrier is needed between
+// raters.  Two lanes can meet on one column only for different raters; they are then added in lane
+// order (= ascending rater), which keeps every accumulator's summation order fixed.
 __global__ void __launch_bounds__(H_THREADS)
-k_build_H(int32_t I_c, int32_t ld, int32_t chunk_w, int32_t nchunk, int32_t slot0,
+k_build_H(int32_t I_c, int32_t ld, int32_t slice_w, int32_t n_bound, int32_t slot0,
           const int32_t* __restrict__ c_start, const int32_t* __restrict__ c_len,
           const double* __restrict__ c_b, const double* __restrict__ c_alpha,
           const int32_t* __restrict__ csc_lu, const double* __restrict__ csc_delta,
           const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ csr_loc,
           const double* __restrict__ csr_delta, double* __restrict__ H) {
     extern __shared__ double acc[];
-    __shared__ int32_t s_lo[H_THREADS], s_hi[H_THREADS];
-    __shared__ double s_d[H_THREADS];
+    __shared__ int32_t s_lu[H_RB];
+    __shared__ double s_d[H_RB];
+    __shared__ int32_t s_b[H_WARPS + 1][H_RB];        // slice boundaries of every staged rater
+    __shared__ int32_t s_off[H_WARPS][H_RB + 1];      // per warp: exclusive prefix of entry counts
     const int32_t j = blockIdx.x;
+    const int32_t chunk_w = slice_w * H_WARPS;
     const int32_t i0 = blockIdx.y * chunk_w;
     const int32_t i1 = min(i0 + chunk_w, I_c);
     const int32_t w = i1 - i0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int32_t t = threadIdx.x; t < w; t += H_THREADS) acc[t] = 0.0;
     const int32_t x0 = c_start[slot0 + j], nr = c_len[slot0 + j];
-    for (int32_t rb = 0; rb < nr; rb += H_THREADS) {
-        const int32_t nb = min(H_THREADS, nr - rb);
+    for (int32_t rb = 0; rb < nr; rb += H_RB) {
+        const int32_t nb = min(H_RB, nr - rb);
         __syncthreads();
-        if (threadIdx.x < nb) {             // stage this batch of raters: range of their row in the chunk
-            const int32_t x = x0 + rb + threadIdx.x;
-            const int32_t lu = csc_lu[x];
-            s_d[threadIdx.x] = csc_delta[x];
-            s_lo[threadIdx.x] = chunk_ptr[lu * (nchunk + 1) + blockIdx.y];
-            s_hi[threadIdx.x] = chunk_ptr[lu * (nchunk + 1) + blockIdx.y + 1];
+        if (threadIdx.x < nb) {
+            s_lu[threadIdx.x] = csc_lu[x0 + rb + threadIdx.x];
+            s_d[threadIdx.x] = csc_delta[x0 + rb + threadIdx.x];
         }
         __syncthreads();
-        for (int32_t r = 0; r < nb; r++) {
-            const int32_t lo = s_lo[r], hi = s_hi[r];
-            if (hi > lo) {                  // uniform over the CTA
-                const double dvj = s_d[r];
-                for (int32_t e = lo + threadIdx.x; e < hi; e += H_THREADS) {
-                    const int32_t t = csr_loc[e] - i0;
-                    acc[t] = __dadd_rn(acc[t], __dmul_rn(dvj, csr_delta[e]));
-                }
-                __syncthreads();
+        for (int32_t idx = threadIdx.x; idx < nb * (H_WARPS + 1); idx += H_THREADS) {
+            const int32_t t = idx / (H_WARPS + 1), q = idx % (H_WARPS + 1);
+            s_b[q][t] = chunk_ptr[(size_t)s_lu[t] * n_bound + blockIdx.y * H_WARPS + q];
+        }
+        __syncthreads();
+        // per-warp exclusive scan of its entry counts over the staged raters (H_RB = 4 * 32)
+        {
+            int32_t c[4], sum = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int t = lane * 4 + q;
+                c[q] = (t < nb) ? (s_b[warp + 1][t] - s_b[warp][t]) : 0;
+                sum += c[q];
             }
+            int32_t incl = sum;
+            for (int o = 1; o < 32; o <<= 1) { const int32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            int32_t run = incl - sum;
+#pragma unroll
+            for (int q = 0; q < 4; q++) { s_off[warp][lane * 4 + q] = run; run += c[q]; }
+            if (lane == 31) s_off[warp][H_RB] = incl;
+        }
+        __syncwarp();
+        const int32_t total = s_off[warp][H_RB];
+        for (int32_t f0 = 0; f0 < total; f0 += 32) {
+            const int32_t f = f0 + lane;
+            const bool valid = f < total;
+            int32_t col = -1 - lane;                    // unique dummy for idle lanes
+            double val = 0.0;
+            if (valid) {
+                int lo = 0, hi = nb;                    // last r with s_off[r] <= f
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[warp][mid] <= f) lo = mid; else hi = mid; }
+                const int32_t e = s_b[warp][lo] + (f - s_off[warp][lo]);
+                col = csr_loc[e] - i0;
+                val = __dmul_rn(s_d[lo], csr_delta[e]);
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, col);
+            if (valid) {
+                if (peers == (1u << lane)) {
+                    acc[col] = __dadd_rn(acc[col], val);
+                } else {                                 // same column from several raters: lane order
+                    const int leader = __ffs(peers) - 1;
+                    double sum = (lane == leader) ? acc[col] : 0.0;
+                    for (unsigned mm = peers; mm; mm &= mm - 1) {
+                        const double v = __shfl_sync(peers, val, __ffs(mm) - 1);
+                        sum = __dadd_rn(sum, v);
+                    }
+                    if (lane == leader) acc[col] = sum;
+                }
+            }
+            __syncwarp();
         }
     }
     __syncthreads();
@@ -405,6 +485,17 @@ k_build_H(int32_t I_c, int32_t ld, int32_t chunk_w, int32_t nchunk, int32_t slot
 // the host from a lower bound on t so that L factors can neither overflow nor underflow), so one
 // log per (u,i) replaces n_u logs (SURVEY.md 7.3 "log throughput").
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t desc_key(double s) {
+    const uint64_t b = (uint64_t)__double_as_longlong(s);
+    const uint64_t asc = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    return ~asc;   // smaller key = larger score
+}
+__device__ __forceinline__ double key_to_score(uint64_t key) {
+    const uint64_t asc = ~key;
+    const uint64_t b = (asc >> 63) ? (asc & 0x7fffffffffffffffull) : ~asc;
+    return __longlong_as_double((long long)b);
+}
+
 __device__ __forceinline__ void peel_exponent(double& p, int& ex) {
     const int hi = __double2hiint(p);
     ex += (hi >> 20) - 1023;
@@ -420,7 +511,7 @@ __global__ void __launch_bounds__(SCORE_THREADS)
 k_score(const double* __restrict__ H, int32_t I_c, int32_t ld, int32_t rank_begin, int32_t slot0,
         const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_loc,
         const double* __restrict__ csr_c, const double* __restrict__ c_b,
-        double log_items, double log_K, double* __restrict__ scores) {
+        double log_items, double log_K, double* __restrict__ scores, unsigned long long* __restrict__ ustat) {
     __shared__ int32_t s_j[SCORE_CHUNK];
     __shared__ double s_c[SCORE_CHUNK];
     __shared__ unsigned s_rated[SCORE_TILE / 32];
@@ -494,6 +585,23 @@ k_score(const double* __restrict__ H, int32_t I_c, int32_t ld, int32_t rank_begi
     if (i + 1 >= I_c) s1 = NANV;
     double2 out; out.x = s0; out.y = s1;
     *reinterpret_cast<double2*>(scores + (size_t)blockIdx.x * ld + i) = out;
+    // per-user candidate count and key range for the radix select (saves k_topn one pass)
+    const bool v0 = (s0 == s0), v1 = (s1 == s1);
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    if (v0) { const unsigned long long k = desc_key(s0); kmin = k; kmax = k; }
+    if (v1) { const unsigned long long k = desc_key(s1); kmin = min(kmin, k); kmax = max(kmax, k); }
+    int cnt = (int)v0 + (int)v1;
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0) {
+        unsigned long long* st = ustat + 3 * (size_t)blockIdx.x;
+        atomicAdd(st, (unsigned long long)cnt);
+        atomicMin(st + 1, kmin);
+        atomicMax(st + 2, kmax);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -501,28 +609,19 @@ k_score(const double* __restrict__ H, int32_t I_c, int32_t ld, int32_t rank_begi
 // sort of the selected (key, index) pairs.  Order = (score desc, item id asc); local index order
 // is item id order.  NaN marks "not a candidate" (rated by the user / padding).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t desc_key(double s) {
-    const uint64_t b = (uint64_t)__double_as_longlong(s);
-    const uint64_t asc = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-    return ~asc;   // smaller key = larger score
-}
-__device__ __forceinline__ double key_to_score(uint64_t key) {
-    const uint64_t asc = ~key;
-    const uint64_t b = (asc >> 63) ? (asc & 0x7fffffffffffffffull) : ~asc;
-    return __longlong_as_double((long long)b);
-}
-
 __global__ void __launch_bounds__(TOPN_THREADS)
-k_topn(const double* __restrict__ scores, int32_t I_c, int32_t ld, int32_t rank_begin, int32_t slot0,
+k_topn(const double* __restrict__ scores, const unsigned long long* __restrict__ ustat,
+       int32_t I_c, int32_t ld, int32_t rank_begin, int32_t slot0,
        int32_t top_n, int32_t out_stride, int32_t filter_users, int32_t split, int32_t n_splits,
        const int32_t* __restrict__ rank_userid, const int32_t* __restrict__ c_item,
        int32_t out_row0, int32_t* __restrict__ out_item, double* __restrict__ out_score,
        int32_t* __restrict__ out_count) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ unsigned s_hist[256];
-    __shared__ unsigned long long s_red[TOPN_THREADS / 32];
-    __shared__ unsigned long long s_kmin, s_kmax;
-    __shared__ int s_cnt, s_digit, s_remaining, s_done, s_nsel, s_eqtaken;
+    constexpr int RBITS = 11, NBINS = 1 << RBITS;             // 4 bins per thread
+    static_assert(NBINS == 4 * TOPN_THREADS, "bucket search assumes 4 bins per thread");
+    __shared__ unsigned s_hist[NBINS];
+    __shared__ int s_wsum[TOPN_THREADS / 32];
+    __shared__ int s_digit, s_remaining, s_done, s_nsel, s_eqtaken;
 
     const int32_t rank = rank_begin + blockIdx.x;
     const int32_t orow = out_row0 + blockIdx.x;
@@ -530,85 +629,70 @@ k_topn(const double* __restrict__ scores, int32_t I_c, int32_t ld, int32_t rank_
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     const int32_t uid = rank_userid[rank];
-    if (uid < filter_users || (n_splits > 1 && (uid % n_splits) != split)) {   // :203-205, :220-223
-        if (tid == 0) out_count[orow] = 0;
-        return;
-    }
-
-    // pass 0: candidate count, min and max key
-    int cnt = 0;
-    uint64_t kmin = ~0ull, kmax = 0ull;
-    for (int32_t i = tid; i < I_c; i += TOPN_THREADS) {
-        const double s = row[i];
-        if (s == s) { const uint64_t k = desc_key(s); cnt++; kmin = min(kmin, k); kmax = max(kmax, k); }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-    }
-    if (tid == 0) { s_cnt = 0; s_kmin = ~0ull; s_kmax = 0ull; }
-    __syncthreads();
-    if (lane == 0) { atomicAdd(&s_cnt, cnt); atomicMin(&s_kmin, (unsigned long long)kmin); atomicMax(&s_kmax, (unsigned long long)kmax); }
-    __syncthreads();
-    const int c_u = s_cnt;
+    const int c_u = (int)ustat[3 * (size_t)blockIdx.x];
     const int n_out = min(top_n, c_u);
-    if (n_out == 0) {                       // "does not have any unrated item in the cluster" :210-213
+    // split filter :203-205, "no unrated item" :210-213, filterUsers :220-223
+    if (uid < filter_users || (n_splits > 1 && (uid % n_splits) != split) || n_out == 0) {
         if (tid == 0) out_count[orow] = 0;
         return;
     }
-    const uint64_t kbase = s_kmin;
-    const uint64_t span = s_kmax - kbase;
-    // radix select on (key - kbase), 8 bits per pass from the highest set bit of the span
-    int top_bit = (span == 0) ? 0 : (64 - __clzll((long long)span));    // number of significant bits
-    uint64_t prefix = 0;       // selected high bits (value of (key-kbase) >> shift)
-    int shift = top_bit;       // bits below `shift` are still undecided
-    if (tid == 0) { s_remaining = n_out; s_done = (n_out == c_u); }
+    const uint64_t kbase = ustat[3 * (size_t)blockIdx.x + 1];
+    const uint64_t span = ustat[3 * (size_t)blockIdx.x + 2] - kbase;
+    // radix select on d = key - kbase, RBITS bits per pass from the highest set bit of the span
+    int shift = (span == 0) ? 0 : (64 - __clzll((long long)span));   // bits below `shift` are undecided
+    uint64_t prefix = 0;                                             // decided value of d >> shift
+    const bool all = (n_out == c_u);
+    if (tid == 0) { s_remaining = n_out; s_done = all ? 1 : 0; }
     __syncthreads();
-    // If everything is selected (n_out == c_u) skip the select entirely.
     while (!s_done && shift > 0) {
-        const int nshift = max(shift - 8, 0);
+        const int nshift = max(shift - RBITS, 0);
         const int width = shift - nshift;
-        if (tid < 256) s_hist[tid] = 0;
+        for (int t = tid; t < NBINS; t += TOPN_THREADS) s_hist[t] = 0;
         __syncthreads();
         for (int32_t i = tid; i < I_c; i += TOPN_THREADS) {
-            const double s = row[i];
-            if (s == s) {
-                const uint64_t d = desc_key(s) - kbase;
-                if ((shift >= 64 ? 0ull : (d >> shift)) == prefix) {
-                    const unsigned dig = (unsigned)((d >> nshift) & ((1u << width) - 1));
-                    // warp-aggregated histogram update
-                    const unsigned peers = __match_any_sync(__activemask(), dig);
-                    if ((__ffs(peers) - 1) == lane) atomicAdd(&s_hist[dig], __popc(peers));
-                }
+            const double sc = row[i];
+            if (sc == sc) {
+                const uint64_t d = desc_key(sc) - kbase;
+                if ((shift >= 64 ? 0ull : (d >> shift)) == prefix)
+                    atomicAdd(&s_hist[(unsigned)((d >> nshift) & ((1u << width) - 1))], 1u);
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            int rem = s_remaining, acc = 0, dsel = 0;
-            const int nb = 1 << width;
-            for (int d = 0; d < nb; d++) {
-                const int h = (int)s_hist[d];
-                if (acc + h >= rem) { dsel = d; break; }
-                acc += h;
+        // block-wide search of the bucket holding the s_remaining-th smallest element
+        const int rem = s_remaining;
+        const int h0 = (int)s_hist[4 * tid], h1 = (int)s_hist[4 * tid + 1], h2 = (int)s_hist[4 * tid + 2], h3 = (int)s_hist[4 * tid + 3];
+        const int mine = h0 + h1 + h2 + h3;
+        int incl = mine;
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s_wsum[wid] = incl;
+        __syncthreads();
+        int excl = incl - mine;
+        for (int q = 0; q < wid; q++) excl += s_wsum[q];
+        if (excl < rem && rem <= excl + mine) {          // exactly one thread
+            const int hh[4] = {h0, h1, h2, h3};
+            int acc = excl;
+            for (int q = 0; q < 4; q++) {
+                if (acc + hh[q] >= rem) {
+                    s_digit = 4 * tid + q;
+                    s_remaining = rem - acc;                      // how many to take from this bucket
+                    if (hh[q] == rem - acc) s_done = 1;          // the whole bucket is taken
+                    break;
+                }
+                acc += hh[q];
             }
-            s_digit = dsel;
-            s_remaining = rem - acc;                       // how many to take from bucket dsel
-            if ((int)s_hist[dsel] == rem - acc) s_done = 1; // the whole bucket is taken
         }
         __syncthreads();
         prefix = (prefix << width) | (uint64_t)s_digit;
         shift = nshift;
         __syncthreads();
     }
-    // Selection rule: with d = key - kbase, q = d >> shift:
-    //   q <  prefix -> selected;  q == prefix -> selected if s_done (whole bucket) else the first
-    //   s_remaining of them in index order (only reachable with shift == 0, i.e. equal keys).
-    const bool all = (n_out == c_u);
+    // Selection rule with q = (key - kbase) >> shift:
+    //   q < prefix -> selected;  q == prefix -> selected if the whole bucket is taken, else the
+    //   first s_remaining of them in index order (only reachable with shift == 0: equal keys, so
+    //   index order = ascending item id is the canonical tie-break).
     const bool whole_bucket = (s_done != 0);
     const int eq_take = s_remaining;
 
-    // gather into shared memory
     int P2 = 1; while (P2 < n_out) P2 <<= 1;
     uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);
     int32_t* si = reinterpret_cast<int32_t*>(smem_raw + (size_t)P2 * sizeof(uint64_t));
@@ -620,9 +704,9 @@ k_topn(const double* __restrict__ scores, int32_t I_c, int32_t ld, int32_t rank_
         bool take = false, eq = false;
         uint64_t key = 0;
         if (i < I_c) {
-            const double s = row[i];
-            if (s == s) {
-                key = desc_key(s);
+            const double sc = row[i];
+            if (sc == sc) {
+                key = desc_key(sc);
                 if (all) take = true;
                 else {
                     const uint64_t q = (shift >= 64) ? 0ull : ((key - kbase) >> shift);
@@ -632,14 +716,12 @@ k_topn(const double* __restrict__ scores, int32_t I_c, int32_t ld, int32_t rank_
             }
         }
         if (!all && !whole_bucket) {
-            // ordered take of the first eq_take "equal" elements (index order = item id order)
+            // ordered take of the first eq_take "equal" elements
             const unsigned bal = __ballot_sync(0xffffffffu, eq);
-            if (lane == 0) s_red[wid] = __popc(bal);
+            if (lane == 0) s_wsum[wid] = __popc(bal);
             __syncthreads();
-            int before = s_eqtaken;
-            for (int q = 0; q < wid; q++) before += (int)s_red[q];
-            int tot = 0;
-            for (int q = 0; q < TOPN_THREADS / 32; q++) tot += (int)s_red[q];
+            int before = s_eqtaken, tot = 0;
+            for (int q = 0; q < TOPN_THREADS / 32; q++) { const int v = s_wsum[q]; if (q < wid) before += v; tot += v; }
             if (eq && before + __popc(bal & ((1u << lane) - 1)) < eq_take) take = true;
             __syncthreads();
             if (tid == 0) s_eqtaken += tot;
@@ -672,6 +754,11 @@ k_topn(const double* __restrict__ scores, int32_t I_c, int32_t ld, int32_t rank_
         out_score[(size_t)orow * out_stride + t] = key_to_score(sk[t]);
     }
     if (tid == 0) out_count[orow] = n_out;
+}
+
+__global__ void k_init_ustat(unsigned long long* __restrict__ ustat, int32_t n) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { ustat[3 * (size_t)i] = 0ull; ustat[3 * (size_t)i + 1] = ~0ull; ustat[3 * (size_t)i + 2] = 0ull; }
 }
 
 __global__ void k_widen_counts(const int32_t* __restrict__ cnt, int32_t n, int64_t* __restrict__ out) {

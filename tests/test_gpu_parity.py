@@ -125,6 +125,20 @@ def test_unordered_ids_sparse_ids_and_nonpositive_scores():
     assert_parity(got, want, REL, "remap")
 
 
+def test_non_dyadic_scores_take_the_sequential_statistics_path():
+    # scores like 3.7f are not multiples of 2^-16: sums depend on the order, so the engine must add
+    # them in the oracle's (= canonical) order; statistics stay bit-exact
+    r = datagen.generate("small")
+    sc = (r.score * np.float32(0.74) + np.float32(0.013)).astype(np.float32)
+    r2 = datagen.Ratings("nd", r.n_users, r.n_items, r.user, r.item, sc, r.cl_user, r.cl_cluster, r.cluster_size, 0)
+    got = gpu_run(r2, 0.1, r.n_items, 15)
+    want = cpu_run(r2, 0.1, r.n_items, 15)
+    assert_parity(got, want, REL, "non-dyadic")
+    us, ip, tot = got["stats"]
+    ous, _, oip, otot = orc.stats(r2.user, r2.item, r2.score, r2.cl_user)
+    assert tot == otot and np.array_equal(us, ous)
+
+
 def test_filter_users(golden_ratings):
     got = gpu_run(golden_ratings, 0.5, 100, 5, filter_users=20)
     want = cpu_run(golden_ratings, 0.5, 100, 5, filter_users=20)
