@@ -226,3 +226,48 @@ def test_size_independent_properties_ml100k():
         eng.run(); b = eng.results()
     assert all(np.array_equal(a[k], b[k]) for k in a)
     assert np.array_equal(a["score64"], out["score64"])
+
+
+def test_reference_style_job_and_sinks(golden, golden_ratings):
+    # reads like T/rm/TestHDFSRM2.java:39-75: build conf, run RM2Job, compare userSum / itemColl / output
+    from filmyou_core_b200.rm2_job import RM2Job, HDFSSink, CassandraSink
+    r = golden_ratings
+    conf = {"numberOfItems": golden["numberOfItems"], "numberOfClusters": golden["numberOfClusters"],
+            "numberOfRecommendations": 1000, "lambda": "0.5", "clusterSplit": 5, "splitSize": 3}
+    job = RM2Job(conf)
+    sink = HDFSSink()
+    job.run(r.user, r.item, r.score, r.cl_user, r.cl_cluster, golden["clusteringCount"], sink=sink)
+    assert np.array_equal(job.userSum, np.array(golden["userSum"]))
+    assert np.max(np.abs(job.itemColl[1:] - np.array(golden["itemColl"]))) <= 1e-18
+    gold = {(int(u), int(i)): s for u, i, s in golden["recommendations"]}
+    assert len(sink.records) == len(gold)
+    for key, val in sink.records:
+        assert abs(gold[key] - float(val)) <= golden["accuracy"]
+    cs = CassandraSink()
+    job.run(r.user, r.item, r.score, r.cl_user, r.cl_cluster, golden["clusteringCount"], sink=cs)
+    # CLUSTERING ORDER BY (relevance DESC, item ASC) inside a user  (T/util/CassandraUtils.java:144-147)
+    for a, b in zip(cs.rows, cs.rows[1:]):
+        if a[0] == b[0]:
+            assert (a[1] > b[1]) or (a[1] == b[1] and a[2] < b[2]) or (np.float32(a[1]) == np.float32(b[1]))
+    job.close()
+    with pytest.raises(RuntimeError):
+        bad = RM2Job(conf)
+        bad.run(r.user, r.item, r.score, r.cl_user, r.cl_cluster, [8, 7, 7, 7, 1])
+
+
+def test_cpp_host_mirror(tmp_path):
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "cpp_host_smoke")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp_host_smoke.cpp"), "-o", exe,
+                           "-L", os.path.join(root, "filmyou_core_b200"), "-lfilmyou_rm2",
+                           "-Wl,-rpath," + os.path.join(root, "filmyou_core_b200")])
+    out = subprocess.check_output([exe], text=True).splitlines()
+    assert out[0] == "totalSum 27.0"                                  # RMTestData2.java:45
+    assert [l for l in out if l.startswith("userSum")] == ["userSum %.1f" % v for v in (9, 3, 3, 5, 7)]
+    r = datagen.from_dense([[5, 0, 0, 1, 2], [4, 3, 1, 0, 0], [0, 0, 2, 4, 5]], [0, 0, 1, 1, 1], [2, 3])
+    want = cpu_run(r, 0.5, 3, 10)
+    recs = [l.split() for l in out if l.startswith("rec")]
+    assert [(int(a[1]), int(a[2])) for a in recs] == list(zip(want["user"].tolist(), want["item"].tolist()))
+    assert np.allclose([float(a[3]) for a in recs], want["score32"], rtol=0, atol=1e-5)
