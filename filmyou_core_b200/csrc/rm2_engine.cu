@@ -112,8 +112,10 @@ struct fy_rm2_ctx {
     DBuf<float> p_s32;
 
     // ---- co-occurrence (config 3) ----
-    DBuf<int32_t> cooc_counts;
-    int32_t cooc_items = 0;
+    DBuf<int32_t> cooc_counts, cooc_iota, cooc_zero, cooc_out_item, cooc_out_cnt;
+    DBuf<uint8_t> cooc_bt;
+    DBuf<double> cooc_out_score;
+    int32_t cooc_items = 0, cooc_ldc = 0;
 
     fy_rm2_profile prof{};
     std::vector<cudaEvent_t> events;
@@ -542,11 +544,10 @@ static int run_pipeline(fy_rm2_ctx* ctx) {
     const size_t SCORE_BUF_BYTES = (size_t)2 << 30;
     auto h_geometry = [&](int32_t I_c, int32_t& ld, int32_t& slice_w, int32_t& chunk_w, int32_t& nchunk, int32_t& n_bound) {
         ld = cdiv(I_c, SCORE_TILE) * SCORE_TILE;
-        nchunk = cdiv(I_c, H_MAX_CHUNK);
-        slice_w = cdiv(cdiv(cdiv(I_c, nchunk), H_WARPS), 8) * 8;
-        chunk_w = slice_w * H_WARPS;
-        nchunk = cdiv(I_c, chunk_w);
-        n_bound = nchunk * H_WARPS + 1;
+        slice_w = H_SLICE;
+        chunk_w = H_SLICE * H_WARPS;
+        nchunk = cdiv(cdiv(I_c, H_SLICE), H_WARPS);     // CTAs per row
+        n_bound = cdiv(I_c, H_SLICE) + 1;               // slice boundaries per user
     };
     {   // size the per-cluster buffers once (growing them inside the loop would synchronise the device)
         size_t need_h = 0, need_cp = 0, need_sc = 0, need_us = 0;
@@ -587,9 +588,8 @@ static int run_pipeline(fy_rm2_ctx* ctx) {
             const size_t k = seg_begin(SEG_GRAM, sG);
             LAUNCH_ON(ctx, sG, k_chunk_ptr, cdiv((int64_t)K_c * n_bound, 256), 256, 0, cs, K_c, n_bound, slice_w,
                       ctx->rowptr.p, ctx->csr_loc.p, ctx->chunk_ptr2[hb].p);
-            const size_t smem = (size_t)chunk_w * sizeof(double);
-            if (smem > 24 * 1024) CK(cudaFuncSetAttribute(k_build_H, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LAUNCH_ON(ctx, sG, k_build_H, dim3(I_c, nchunk), H_THREADS, smem, I_c, ld, slice_w, n_bound, slot0,
+            const size_t smem = (size_t)chunk_w * sizeof(double);      // 32 KB: 8 warps x 512 doubles
+            LAUNCH_ON(ctx, sG, k_build_H, dim3(I_c, nchunk), H_THREADS, smem, I_c, ld, n_bound - 1, slot0,
                       ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, ctx->c_alpha.p, ctx->csc_lu.p, ctx->csc_delta.p,
                       ctx->chunk_ptr2[hb].p, ctx->csr_loc.p, ctx->csr_delta.p, ctx->H[hb].p);
             seg_end(k, sG);
@@ -800,5 +800,88 @@ extern "C" int fy_rm2_score_group(fy_rm2_ctx* ctx, int32_t cluster_id, int32_t s
 }
 
 // ---------------------------------------------------------------------------------------------
-// config 3 entry points live in cooc_tcgen05.cu
+// config 3: item-item co-occurrence (GEMM kernel + launcher in cooc_tcgen05.cu)
 // ---------------------------------------------------------------------------------------------
+extern "C" int fyi_cooc_gemm_launch(const uint8_t* Bt, int n_items, int k_pad, int32_t* C, int ldc, void* stream,
+                                    char* err, size_t errlen);
+
+extern "C" int fy_cooc_counts(fy_rm2_ctx* ctx, int32_t n_user_ids, int32_t n_items, int32_t* counts_out, double* ms_gemm_out) {
+    if (!ctx) return FY_E_ARG;
+    if (!ctx->have_ratings) return ctx->fail(FY_E_STATE, "fy_cooc_counts needs fy_rm2_set_ratings first");
+    if (n_user_ids <= 0 || n_items <= ctx->max_item) return ctx->fail(FY_E_ARG, "n_items must exceed the largest rated item id (%d)", ctx->max_item);
+    return guarded(ctx, [&]() {
+        using namespace fy;
+        CK(cudaSetDevice(ctx->prm.device));
+        cudaStream_t st = ctx->stream;
+        const int32_t k_pad = cdiv(n_user_ids, 128) * 128, ldc = cdiv(n_items, 256) * 256;
+        ctx->cooc_bt.need((size_t)n_items * k_pad);
+        ctx->cooc_counts.need((size_t)n_items * ldc);
+        ctx->flags.need(DF_COUNT);
+        CK(cudaMemsetAsync(ctx->flags.p, 0, sizeof(int) * DF_COUNT, st));
+        CK(cudaMemsetAsync(ctx->cooc_bt.p, 0, (size_t)n_items * k_pad, st));
+        LAUNCH(ctx, k_binarise, cdiv(ctx->nnz, 256), 256, 0, ctx->in_user.p, ctx->in_item.p, ctx->in_score.p, ctx->nnz,
+               n_user_ids, n_items, k_pad, ctx->cooc_bt.p, ctx->flags.p);
+        cudaEvent_t e0 = ctx->ev(0), e1 = ctx->ev(1);
+        CK(cudaEventRecord(e0, st));
+        const int rc = fyi_cooc_gemm_launch(ctx->cooc_bt.p, n_items, k_pad, ctx->cooc_counts.p, ldc, (void*)st, ctx->err, sizeof(ctx->err));
+        if (rc != 0) return rc;
+        ctx->launches++;
+        CK(cudaEventRecord(e1, st));
+        int h_flags[DF_COUNT];
+        CK(cudaMemcpyAsync(h_flags, ctx->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_flags[DF_BAD_ITEM]) return ctx->fail(FY_E_ARG, "user or item id outside [0, n_user_ids) x [0, n_items)");
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms_gemm_out) *ms_gemm_out = ms;
+        ctx->cooc_items = n_items; ctx->cooc_ldc = ldc;
+        if (counts_out)
+            CK(cudaMemcpy2D(counts_out, (size_t)n_items * 4, ctx->cooc_counts.p, (size_t)ldc * 4, (size_t)n_items * 4, n_items, cudaMemcpyDeviceToHost));
+        return (int)FY_OK;
+    });
+}
+
+extern "C" int fy_cooc_topk(fy_rm2_ctx* ctx, int32_t k, int32_t* item_out, int32_t* count_out, int32_t* n_out) {
+    if (!ctx) return FY_E_ARG;
+    if (ctx->cooc_items <= 0) return ctx->fail(FY_E_STATE, "fy_cooc_topk needs fy_cooc_counts first");
+    if (k <= 0 || k > fy::TOPN_MAX_SELECT) return ctx->fail(FY_E_UNSUPPORTED, "k outside [1, %d]", fy::TOPN_MAX_SELECT);
+    return guarded(ctx, [&]() {
+        using namespace fy;
+        CK(cudaSetDevice(ctx->prm.device));
+        cudaStream_t st = ctx->stream;
+        const int32_t n = ctx->cooc_items, ldc = ctx->cooc_ldc, ld = cdiv(n, SCORE_TILE) * SCORE_TILE;
+        const int32_t batch = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)1 << 30) / ((size_t)ld * 8)));
+        ctx->scores[0].need((size_t)batch * ld); ctx->ustat[0].need((size_t)batch * 3);
+        ctx->cooc_iota.need(n); ctx->cooc_zero.need(n);
+        ctx->cooc_out_item.need((size_t)n * k); ctx->cooc_out_score.need((size_t)n * k); ctx->cooc_out_cnt.need(n);
+        LAUNCH(ctx, k_iota, cdiv(n, 256), 256, 0, ctx->cooc_iota.p, n);
+        CK(cudaMemsetAsync(ctx->cooc_zero.p, 0, (size_t)n * 4, st));
+        CK(cudaMemsetAsync(ctx->cooc_out_cnt.p, 0, (size_t)n * 4, st));
+        int P2 = 1; while (P2 < std::min(k, n)) P2 <<= 1;
+        const size_t topn_smem = (size_t)P2 * 12;
+        if (topn_smem > 36 * 1024) CK(cudaFuncSetAttribute(k_topn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topn_smem));
+        for (int32_t r0 = 0; r0 < n; r0 += batch) {
+            const int32_t nb = std::min(batch, n - r0);
+            LAUNCH(ctx, k_init_ustat, cdiv(nb, 256), 256, 0, ctx->ustat[0].p, nb);
+            LAUNCH(ctx, k_cooc_scores, dim3(nb, ld / SCORE_TILE), SCORE_THREADS, 0, ctx->cooc_counts.p, n, ldc, ld, r0,
+                   ctx->scores[0].p, ctx->ustat[0].p);
+            LAUNCH(ctx, k_topn, nb, TOPN_THREADS, topn_smem, ctx->scores[0].p, ctx->ustat[0].p, n, ld, 0, 0, k, k, 0, 0, 1,
+                   ctx->cooc_zero.p, ctx->cooc_iota.p, r0, ctx->cooc_out_item.p, ctx->cooc_out_score.p, ctx->cooc_out_cnt.p);
+        }
+        std::vector<double> sc((size_t)n * k);
+        std::vector<int32_t> cnt((size_t)n);
+        CK(cudaMemcpyAsync(item_out, ctx->cooc_out_item.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(sc.data(), ctx->cooc_out_score.p, (size_t)n * k * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(cnt.data(), ctx->cooc_out_cnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int32_t r = 0; r < n; r++) {
+            if (n_out) n_out[r] = cnt[r];
+            for (int32_t t = 0; t < k; t++) {
+                const size_t o = (size_t)r * k + t;
+                if (t < cnt[r]) { if (count_out) count_out[o] = (int32_t)sc[o]; }
+                else { item_out[o] = -1; if (count_out) count_out[o] = 0; }
+            }
+        }
+        return (int)FY_OK;
+    });
+}

@@ -35,10 +35,9 @@ enum DevFlag : int {
 constexpr int SCORE_TILE = 256;     // candidates per score CTA (2 per thread)
 constexpr int SCORE_THREADS = 128;
 constexpr int SCORE_CHUNK = 512;    // rated items staged in shared memory at a time
-constexpr int H_MAX_CHUNK = 12288;  // columns of one H row accumulated per CTA (<= 96 KB of doubles)
-constexpr int H_THREADS = 512;
-constexpr int H_WARPS = H_THREADS / 32;   // each warp owns one contiguous column slice of the chunk
-constexpr int H_RB = 128;           // raters staged per batch
+constexpr int H_SLICE = 512;        // columns of one H row built by one warp (4 KB of doubles)
+constexpr int H_THREADS = 256;
+constexpr int H_WARPS = H_THREADS / 32;   // 8 independent (row, slice) tasks per CTA
 constexpr int TOPN_THREADS = 512;
 constexpr int TOPN_MAX_SELECT = 4096;
 
@@ -384,79 +383,72 @@ __global__ void k_chunk_ptr(int32_t rank0, int32_t K_c, int32_t n_bound, int32_t
     chunk_ptr[idx] = a;
 }
 
-// CTA = (row j, column chunk of H_WARPS slices).  Warp w owns slice w of the chunk: it walks the
-// flattened list of (rater of j, that rater's entries inside the slice) 32 at a time, so lanes stay
-// busy however few entries one rater has in the slice, and no block barrier is needed between
-// raters.  Two lanes can meet on one column only for different raters; they are then added in lane
-// order (= ascending rater), which keeps every accumulator's summation order fixed.
+// One WARP builds one (row j, 512-column slice) of H; a CTA is just 8 such independent tasks, so
+// there is no block barrier anywhere and ~56 warps per SM hide each other's latency.
+// The warp walks the flattened list of (rater of j, that rater's entries inside the slice) 32
+// entries at a time: the raters of j are taken 32 at a time, lane r holding rater r's delta and
+// entry range; a 5-step shuffle binary search maps a flat position to its rater.  Two lanes can
+// meet on one column only for different raters; they are then added in lane order (= ascending
+// rater), so every accumulator's summation order is fixed.
 __global__ void __launch_bounds__(H_THREADS)
-k_build_H(int32_t I_c, int32_t ld, int32_t slice_w, int32_t n_bound, int32_t slot0,
+k_build_H(int32_t I_c, int32_t ld, int32_t n_slices, int32_t slot0,
           const int32_t* __restrict__ c_start, const int32_t* __restrict__ c_len,
           const double* __restrict__ c_b, const double* __restrict__ c_alpha,
           const int32_t* __restrict__ csc_lu, const double* __restrict__ csc_delta,
           const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ csr_loc,
           const double* __restrict__ csr_delta, double* __restrict__ H) {
-    extern __shared__ double acc[];
-    __shared__ int32_t s_lu[H_RB];
-    __shared__ double s_d[H_RB];
-    __shared__ int32_t s_b[H_WARPS + 1][H_RB];        // slice boundaries of every staged rater
-    __shared__ int32_t s_off[H_WARPS][H_RB + 1];      // per warp: exclusive prefix of entry counts
-    const int32_t j = blockIdx.x;
-    const int32_t chunk_w = slice_w * H_WARPS;
-    const int32_t i0 = blockIdx.y * chunk_w;
-    const int32_t i1 = min(i0 + chunk_w, I_c);
-    const int32_t w = i1 - i0;
+    extern __shared__ double acc_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int32_t t = threadIdx.x; t < w; t += H_THREADS) acc[t] = 0.0;
+    const int32_t j = blockIdx.x;
+    const int32_t sl = blockIdx.y * H_WARPS + warp;
+    if (sl >= n_slices) return;
+    double* __restrict__ acc = acc_all + warp * H_SLICE;
+    const int32_t c0 = sl * H_SLICE;
+    const int32_t w = min(H_SLICE, I_c - c0);
+    const int32_t n_bound = n_slices + 1;
+#pragma unroll
+    for (int t = lane * 2; t < H_SLICE; t += 64) *reinterpret_cast<double2*>(acc + t) = make_double2(0.0, 0.0);
+    __syncwarp();
     const int32_t x0 = c_start[slot0 + j], nr = c_len[slot0 + j];
-    for (int32_t rb = 0; rb < nr; rb += H_RB) {
-        const int32_t nb = min(H_RB, nr - rb);
-        __syncthreads();
-        if (threadIdx.x < nb) {
-            s_lu[threadIdx.x] = csc_lu[x0 + rb + threadIdx.x];
-            s_d[threadIdx.x] = csc_delta[x0 + rb + threadIdx.x];
+    for (int32_t g = 0; g < nr; g += 32) {
+        // lane r: rater g+r of row j
+        int32_t lo = 0, cnt = 0;
+        double d = 0.0;
+        if (g + lane < nr) {
+            const int32_t x = x0 + g + lane;
+            const size_t bp = (size_t)csc_lu[x] * n_bound + sl;
+            d = csc_delta[x];
+            lo = chunk_ptr[bp];
+            cnt = chunk_ptr[bp + 1] - lo;
         }
-        __syncthreads();
-        for (int32_t idx = threadIdx.x; idx < nb * (H_WARPS + 1); idx += H_THREADS) {
-            const int32_t t = idx / (H_WARPS + 1), q = idx % (H_WARPS + 1);
-            s_b[q][t] = chunk_ptr[(size_t)s_lu[t] * n_bound + blockIdx.y * H_WARPS + q];
-        }
-        __syncthreads();
-        // per-warp exclusive scan of its entry counts over the staged raters (H_RB = 4 * 32)
-        {
-            int32_t c[4], sum = 0;
+        int32_t incl = cnt;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int t = lane * 4 + q;
-                c[q] = (t < nb) ? (s_b[warp + 1][t] - s_b[warp][t]) : 0;
-                sum += c[q];
-            }
-            int32_t incl = sum;
-            for (int o = 1; o < 32; o <<= 1) { const int32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            int32_t run = incl - sum;
-#pragma unroll
-            for (int q = 0; q < 4; q++) { s_off[warp][lane * 4 + q] = run; run += c[q]; }
-            if (lane == 31) s_off[warp][H_RB] = incl;
-        }
-        __syncwarp();
-        const int32_t total = s_off[warp][H_RB];
+        for (int o = 1; o < 32; o <<= 1) { const int32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int32_t off = incl - cnt;                                   // exclusive prefix
+        const int32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const int32_t ebase = lo - off;                                   // entry = ebase[r] + f
         for (int32_t f0 = 0; f0 < total; f0 += 32) {
             const int32_t f = f0 + lane;
             const bool valid = f < total;
-            int32_t col = -1 - lane;                    // unique dummy for idle lanes
+            int r = 0;                                                    // largest r with off[r] <= f
+#pragma unroll
+            for (int st = 16; st > 0; st >>= 1) {
+                const int32_t v = __shfl_sync(0xffffffffu, off, r + st);
+                if (v <= f) r += st;
+            }
+            const int32_t e = __shfl_sync(0xffffffffu, ebase, r) + f;
+            const double dr = __shfl_sync(0xffffffffu, d, r);
+            int32_t col = -1 - lane;                                      // unique dummy for idle lanes
             double val = 0.0;
             if (valid) {
-                int lo = 0, hi = nb;                    // last r with s_off[r] <= f
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[warp][mid] <= f) lo = mid; else hi = mid; }
-                const int32_t e = s_b[warp][lo] + (f - s_off[warp][lo]);
-                col = csr_loc[e] - i0;
-                val = __dmul_rn(s_d[lo], csr_delta[e]);
+                col = csr_loc[e] - c0;
+                val = __dmul_rn(dr, csr_delta[e]);
             }
             const unsigned peers = __match_any_sync(0xffffffffu, col);
             if (valid) {
                 if (peers == (1u << lane)) {
                     acc[col] = __dadd_rn(acc[col], val);
-                } else {                                 // same column from several raters: lane order
+                } else {                                                  // several raters, one column
                     const int leader = __ffs(peers) - 1;
                     double sum = (lane == leader) ? acc[col] : 0.0;
                     for (unsigned mm = peers; mm; mm &= mm - 1) {
@@ -469,13 +461,21 @@ k_build_H(int32_t I_c, int32_t ld, int32_t slice_w, int32_t n_bound, int32_t slo
             __syncwarp();
         }
     }
-    __syncthreads();
     const double bj = c_b[slot0 + j];
-    double* __restrict__ row = H + (size_t)j * ld;
-    for (int32_t t = threadIdx.x; t < w; t += H_THREADS)
-        row[i0 + t] = __fma_rn(bj, c_alpha[slot0 + i0 + t], acc[t]);
-    if (blockIdx.y == gridDim.y - 1)
-        for (int32_t i = I_c + threadIdx.x; i < ld; i += H_THREADS) row[i] = 1.0;   // padding columns
+    double* __restrict__ row = H + (size_t)j * ld + c0;
+    const double* __restrict__ al = c_alpha + slot0 + c0;
+    for (int t = lane * 2; t < w; t += 64) {
+        if (t + 1 < w) {
+            double2 o;
+            o.x = __fma_rn(bj, al[t], acc[t]);
+            o.y = __fma_rn(bj, al[t + 1], acc[t + 1]);
+            *reinterpret_cast<double2*>(row + t) = o;
+        } else {
+            row[t] = __fma_rn(bj, al[t], acc[t]);
+        }
+    }
+    if (sl == n_slices - 1)
+        for (int32_t i = I_c + lane; i < ld; i += 32) H[(size_t)j * ld + i] = 1.0;   // padding columns
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -759,6 +759,56 @@ k_topn(const double* __restrict__ scores, const unsigned long long* __restrict__
 __global__ void k_init_ustat(unsigned long long* __restrict__ ustat, int32_t n) {
     const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { ustat[3 * (size_t)i] = 0ull; ustat[3 * (size_t)i + 1] = ~0ull; ustat[3 * (size_t)i + 2] = 0ull; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Config 3 helpers (the GEMM itself is in cooc_tcgen05.cu)
+// ---------------------------------------------------------------------------------------------
+// binarised, transposed rating matrix Bt[item][user] (uint8, row pitch k_pad); score > 0 only
+__global__ void k_binarise(const int32_t* __restrict__ r_user, const int32_t* __restrict__ r_item,
+                           const float* __restrict__ r_score, int64_t nnz, int32_t n_user_ids, int32_t n_items,
+                           int32_t k_pad, uint8_t* __restrict__ Bt, int* __restrict__ flags) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz || !(r_score[e] > 0.0f)) return;
+    const int32_t u = r_user[e], i = r_item[e];
+    if (u < 0 || u >= n_user_ids || i < 0 || i >= n_items) { atomicOr(&flags[DF_BAD_ITEM], 1); return; }
+    Bt[(size_t)i * k_pad + u] = 1;
+}
+
+// rows [row0, row0+gridDim.x) of the count matrix -> score rows for k_topn: NaN for the item itself
+// (excludeSelfSimilarity) and for zero counts (RowSimilarityJob emits no zero similarities)
+__global__ void __launch_bounds__(SCORE_THREADS)
+k_cooc_scores(const int32_t* __restrict__ C, int32_t n_items, int32_t ldc, int32_t ld, int32_t row0,
+              double* __restrict__ scores, unsigned long long* __restrict__ ustat) {
+    const int32_t row = row0 + blockIdx.x;
+    const int32_t i = blockIdx.y * SCORE_TILE + 2 * threadIdx.x;
+    const double NANV = __longlong_as_double(0x7ff8000000000000ll);
+    double s0 = NANV, s1 = NANV;
+    if (i < n_items && i != row) { const int32_t c = C[(size_t)row * ldc + i]; if (c > 0) s0 = (double)c; }
+    if (i + 1 < n_items && i + 1 != row) { const int32_t c = C[(size_t)row * ldc + i + 1]; if (c > 0) s1 = (double)c; }
+    double2 out; out.x = s0; out.y = s1;
+    *reinterpret_cast<double2*>(scores + (size_t)blockIdx.x * ld + i) = out;
+    const bool v0 = (s0 == s0), v1 = (s1 == s1);
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    if (v0) { const unsigned long long k = desc_key(s0); kmin = k; kmax = k; }
+    if (v1) { const unsigned long long k = desc_key(s1); kmin = min(kmin, k); kmax = max(kmax, k); }
+    int cnt = (int)v0 + (int)v1;
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0) {
+        unsigned long long* st = ustat + 3 * (size_t)blockIdx.x;
+        atomicAdd(st, (unsigned long long)cnt);
+        atomicMin(st + 1, kmin);
+        atomicMax(st + 2, kmax);
+    }
+}
+
+__global__ void k_iota(int32_t* __restrict__ p, int32_t n) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
 }
 
 __global__ void k_widen_counts(const int32_t* __restrict__ cnt, int32_t n, int64_t* __restrict__ out) {

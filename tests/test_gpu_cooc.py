@@ -1,0 +1,50 @@
+"""GPU suite, config 3: item-item co-occurrence counts as an int8 tcgen05 GEMM,
+bit-exact against the integer CPU oracle.  PARITY UNPINNED w.r.t. the reference: the arithmetic lives
+in Mahout 0.8 (RowSimilarityJob / CooccurrenceCountSimilarity), which /root/reference does not vendor
+and no reference test touches; the oracle restates Mahout's published definition."""
+import numpy as np
+import pytest
+
+import filmyou_core_b200 as fy
+from filmyou_core_b200 import datagen
+from oracle import rm2_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _topk_ref(C, k):
+    n = C.shape[0]
+    items = -np.ones((n, k), np.int32); counts = np.zeros((n, k), np.int32); cnt = np.zeros(n, np.int32)
+    for i in range(n):
+        row = C[i].astype(np.int64).copy()
+        row[i] = 0                                        # excludeSelfSimilarity
+        nz = np.flatnonzero(row > 0)
+        order = nz[np.lexsort((nz, -row[nz]))][:k]        # count desc, item id asc
+        items[i, :len(order)] = order; counts[i, :len(order)] = row[order]; cnt[i] = len(order)
+    return items, counts, cnt
+
+
+@pytest.mark.parametrize("shape", ["tiny", "small", "ml-100k", "ml-1m"])
+def test_counts_bit_exact(shape):
+    r = datagen.generate(shape)
+    n_u, n_i = r.n_users + 1, r.n_items + 1               # ids are 1-based
+    with fy.Rm2Engine(number_of_items=r.n_items) as eng:
+        eng.set_ratings(r.user, r.item, r.score)
+        got, ms = eng.cooc_counts(n_u, n_i)
+        want = orc.cooccurrence(r.user, r.item, r.score, n_u, n_i)
+        assert np.array_equal(got, want)
+        assert np.array_equal(got, got.T) and got.diagonal().sum() == r.nnz   # symmetry, diag = item popularity
+        if shape in ("tiny", "small", "ml-100k"):
+            items, counts, cnt = eng.cooc_topk(n_i, 100)
+            wi, wc, wn = _topk_ref(want, 100)
+            assert np.array_equal(cnt, wn) and np.array_equal(items, wi) and np.array_equal(counts, wc)
+
+
+def test_nonpositive_scores_and_duplicates_are_binarised():
+    user = np.array([0, 0, 1, 1, 1, 2, 2], np.int32)
+    item = np.array([0, 1, 0, 1, 1, 2, 0], np.int32)
+    score = np.array([1, 2, 3, 4, 5, 0, -1], np.float32)     # last two ignored; (1,1) twice counts once
+    with fy.Rm2Engine(number_of_items=3) as eng:
+        eng.set_ratings(user, item, score)
+        got, _ = eng.cooc_counts(3, 3)
+    assert got.tolist() == [[2, 2, 0], [2, 2, 0], [0, 0, 0]]
