@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--workload", default="ml-20m")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--score-mode", type=int, default=0, help="0 = hi-word stream + exact re-score (default), 1 = fp64 stream")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -219,7 +220,7 @@ def main():
         torch.cuda.synchronize()
 
     eng = fy.Rm2Engine(lam=LAMBDA, number_of_items=r.n_items, top_n=TOP_N, device=local_rank,
-                       shard_rank=rank, shard_count=world)
+                       shard_rank=rank, shard_count=world, score_mode=args.score_mode)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)          # torch.cuda.Event then times the launching stream
 

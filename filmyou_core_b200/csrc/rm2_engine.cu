@@ -97,6 +97,10 @@ struct fy_rm2_ctx {
 
     // ---- per cluster ----
     DBuf<double> H[2], scores[2];
+    DBuf<uint32_t> Hh[2];
+    DBuf<int32_t> cand[2], cand_cnt[2];
+    DBuf<double> cand_score[2];
+    DBuf<int> overflow;
     DBuf<int32_t> chunk_ptr2[2];
     cudaStream_t stream_g = nullptr, stream_t = nullptr;   // H build / top-N run beside the score stream
     cudaEvent_t sync_ev[10] = {nullptr};
@@ -174,12 +178,13 @@ extern "C" void fy_rm2_default_params(fy_rm2_params* p) {
     p->shard_rank = 0;
     p->shard_count = 1;
     p->tie_break = 0;
+    p->score_mode = 0;
 }
 
 extern "C" int fy_rm2_create(fy_rm2_ctx** out, const fy_rm2_params* p) {
     if (!out || !p) return FY_E_ARG;
     *out = nullptr;
-    if (p->top_n < 0 || p->number_of_items <= 0 || p->tie_break != 0 || !(p->lambda >= 0.0 && p->lambda <= 1.0))
+    if (p->top_n < 0 || p->number_of_items <= 0 || p->tie_break != 0 || p->score_mode < 0 || p->score_mode > 1 || !(p->lambda >= 0.0 && p->lambda <= 1.0))
         return FY_E_ARG;
     if (p->shard_count < 0 || (p->shard_count > 1 && (p->shard_rank < 0 || p->shard_rank >= p->shard_count)))
         return FY_E_ARG;
@@ -346,7 +351,7 @@ static void launch_score(fy_rm2_ctx* ctx, cudaStream_t strm, dim3 grid, const do
               ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, log_items, log_K, scores, ustat);
 }
 
-static int run_pipeline(fy_rm2_ctx* ctx) {
+static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     using namespace fy;
     if (!ctx->have_ratings || !ctx->have_clustering) return ctx->fail(FY_E_STATE, "fy_rm2_run needs fy_rm2_set_ratings and fy_rm2_set_clustering first");
     CK(cudaSetDevice(ctx->prm.device));
@@ -519,6 +524,14 @@ static int run_pipeline(fy_rm2_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->out_count.p, 0, ((size_t)std::max(n_rows, 1) + 1) * 4, st));
     const double log_items = std::log((double)ctx->prm.number_of_items);   // AbstractRM2Reducer.java:328
 
+    // auto mode: approximate stream over the hi-word plane + exact re-score of the candidates
+    const bool use_hi = (ctx->prm.score_mode == 0) && !force_exact && L >= 2 && out_stride + 32 <= TOPN_MAX_SELECT;
+    int cap = 64; while (cap < out_stride + 32) cap <<= 1;
+    ctx->overflow.need(1);
+    CK(cudaMemsetAsync(ctx->overflow.p, 0, sizeof(int), st));
+    ctx->prof.bytes_per_term = use_hi ? 4.0 : 8.0;
+    ctx->prof.exact_rerun = force_exact ? 1 : 0;
+
     // Three streams: H build of cluster c+1 (latency / DRAM-write bound) and top-N of cluster c-1 run
     // beside the score kernel of cluster c (L1/L2-fabric bound); H and the score matrix are double
     // buffered.  Each stage is timed with events on its own stream.
@@ -536,14 +549,14 @@ static int run_pipeline(fy_rm2_ctx* ctx) {
     CK(cudaEventRecord(evFork, st));
     CK(cudaStreamWaitEvent(sG, evFork, 0));
     CK(cudaStreamWaitEvent(sT, evFork, 0));
-    enum { SEG_GRAM = 0, SEG_SCORE = 1, SEG_TOPN = 2 };
+    enum { SEG_GRAM = 0, SEG_SCORE = 1, SEG_TOPN = 2, SEG_REFINE = 3 };
     struct Seg { int kind; size_t e0, e1; };
     std::vector<Seg> segs;
     auto seg_begin = [&](int kind, cudaStream_t strm) { CK(cudaEventRecord(ctx->ev(evi), strm)); segs.push_back(Seg{kind, evi, 0}); evi++; return segs.size() - 1; };
     auto seg_end = [&](size_t k, cudaStream_t strm) { CK(cudaEventRecord(ctx->ev(evi), strm)); segs[k].e1 = evi; evi++; };
     const size_t SCORE_BUF_BYTES = (size_t)2 << 30;
     auto h_geometry = [&](int32_t I_c, int32_t& ld, int32_t& slice_w, int32_t& chunk_w, int32_t& nchunk, int32_t& n_bound) {
-        ld = cdiv(I_c, SCORE_TILE) * SCORE_TILE;
+        ld = cdiv(I_c, SCOREH_TILE) * SCOREH_TILE;
         slice_w = H_SLICE;
         chunk_w = H_SLICE * H_WARPS;
         nchunk = cdiv(cdiv(I_c, H_SLICE), H_WARPS);     // CTAs per row
@@ -569,6 +582,7 @@ static int run_pipeline(fy_rm2_ctx* ctx) {
             if (b == 1 && n_touched < 2) need_h = need_cp = 0;     // a single cluster needs one H
             if (b == 1 && n_batches < 2) need_sc = need_us = 0;
             ctx->H[b].need(need_h); ctx->chunk_ptr2[b].need(need_cp); ctx->scores[b].need(need_sc); ctx->ustat[b].need(need_us);
+            if (use_hi) { ctx->Hh[b].need(need_h); ctx->cand[b].need(need_us / 3 * cap); ctx->cand_score[b].need(need_us / 3 * cap); ctx->cand_cnt[b].need(need_us / 3); }
         }
     }
     int hb = 0, sb = 0;
@@ -591,7 +605,8 @@ static int run_pipeline(fy_rm2_ctx* ctx) {
             const size_t smem = (size_t)chunk_w * sizeof(double);      // 32 KB: 8 warps x 512 doubles
             LAUNCH_ON(ctx, sG, k_build_H, dim3(I_c, nchunk), H_THREADS, smem, I_c, ld, n_bound - 1, slot0,
                       ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, ctx->c_alpha.p, ctx->csc_lu.p, ctx->csc_delta.p,
-                      ctx->chunk_ptr2[hb].p, ctx->csr_loc.p, ctx->csr_delta.p, ctx->H[hb].p);
+                      ctx->chunk_ptr2[hb].p, ctx->csr_loc.p, ctx->csr_delta.p, ctx->H[hb].p,
+                      use_hi ? ctx->Hh[hb].p : (uint32_t*)nullptr);
             seg_end(k, sG);
         }
         CK(cudaEventRecord(hReady[hb], sG));
@@ -603,18 +618,27 @@ static int run_pipeline(fy_rm2_ctx* ctx) {
         int P2 = 1; while (P2 < std::min(ctx->prm.top_n, I_c)) P2 <<= 1;
         const size_t topn_smem = (size_t)P2 * 12;
         if (topn_smem > 36 * 1024) CK(cudaFuncSetAttribute(k_topn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topn_smem));
+        if (use_hi && (size_t)cap * 12 > 40 * 1024) CK(cudaFuncSetAttribute(k_refine_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 12));
         for (int32_t b0 = r0; b0 < r1; b0 += batch) {
             const int32_t nb = std::min(batch, r1 - b0);
-            const dim3 grid(nb, ld / SCORE_TILE);
+            const dim3 grid(nb, use_hi ? ld / SCOREH_TILE : ld / SCORE_TILE);
             if (s_used[sb]) CK(cudaStreamWaitEvent(sS, sFree[sb], 0));
             LAUNCH_ON(ctx, sS, k_init_ustat, cdiv(nb, 256), 256, 0, ctx->ustat[sb].p, nb);
             {
                 const size_t k = seg_begin(SEG_SCORE, sS);
-                switch (L) {
-                    case 8: launch_score<8>(ctx, sS, grid, ctx->H[hb].p, I_c, ld, b0, slot0, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
-                    case 4: launch_score<4>(ctx, sS, grid, ctx->H[hb].p, I_c, ld, b0, slot0, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
-                    case 2: launch_score<2>(ctx, sS, grid, ctx->H[hb].p, I_c, ld, b0, slot0, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
-                    default: launch_score<1>(ctx, sS, grid, ctx->H[hb].p, I_c, ld, b0, slot0, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
+                if (use_hi) {
+                    switch (L) {
+                        case 8: LAUNCH_ON(ctx, sS, k_score_hi<8>, grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
+                        case 4: LAUNCH_ON(ctx, sS, k_score_hi<4>, grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
+                        default: LAUNCH_ON(ctx, sS, k_score_hi<2>, grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
+                    }
+                } else {
+                    switch (L) {
+                        case 8: launch_score<8>(ctx, sS, grid, ctx->H[hb].p, I_c, ld, b0, slot0, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
+                        case 4: launch_score<4>(ctx, sS, grid, ctx->H[hb].p, I_c, ld, b0, slot0, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
+                        case 2: launch_score<2>(ctx, sS, grid, ctx->H[hb].p, I_c, ld, b0, slot0, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
+                        default: launch_score<1>(ctx, sS, grid, ctx->H[hb].p, I_c, ld, b0, slot0, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
+                    }
                 }
                 seg_end(k, sS);
             }
@@ -629,10 +653,22 @@ static int run_pipeline(fy_rm2_ctx* ctx) {
                           ctx->c_item.p, b0 - ub, ctx->out_item.p, ctx->out_score.p, ctx->out_count.p);
                 seg_end(k, sT);
             }
+            if (use_hi) {
+                const size_t k = seg_begin(SEG_REFINE, sT);
+                LAUNCH_ON(ctx, sT, k_margin_gather, nb, 256, 0, ctx->scores[sb].p, I_c, ld, b0, ub, ctx->rowptr.p, out_stride,
+                          ctx->out_score.p, ctx->out_count.p, cap, ctx->cand[sb].p, ctx->cand_cnt[sb].p, ctx->overflow.p);
+                LAUNCH_ON(ctx, sT, k_refine_score, dim3(nb, cdiv(cap, REFINE_THREADS / 32)), REFINE_THREADS, 0, ctx->H[hb].p, ld, b0,
+                          slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, log_items, log_K, cap, ctx->cand[sb].p,
+                          ctx->cand_cnt[sb].p, ctx->cand_score[sb].p);
+                LAUNCH_ON(ctx, sT, k_refine_sort, nb, REFINE_THREADS, (size_t)cap * 12, b0, ub, slot0, ctx->c_item.p, cap,
+                          ctx->cand[sb].p, ctx->cand_cnt[sb].p, ctx->cand_score[sb].p, out_stride, ctx->out_item.p,
+                          ctx->out_score.p, ctx->out_count.p);
+                seg_end(k, sT);
+            }
             CK(cudaEventRecord(sFree[sb], sT));
             if (ctx->scores[1].cap) sb ^= 1;
         }
-        CK(cudaEventRecord(hFree[hb], sS));
+        CK(cudaEventRecord(hFree[hb], use_hi ? sT : sS));     // the exact re-score reads H too
         if (ctx->H[1].cap) hb ^= 1;
         ctx->prof.clusters_touched++;
     }
@@ -651,7 +687,10 @@ static int run_pipeline(fy_rm2_ctx* ctx) {
     }
     int64_t total_out = 0;
     if (n_rows > 0) CK(cudaMemcpyAsync(&total_out, ctx->out_off.p + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    int h_overflow = 0;
+    CK(cudaMemcpyAsync(&h_overflow, ctx->overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));   // sync C: number of result triples
+    if (use_hi && h_overflow > 0) return 1;      // a candidate list overflowed: redo in exact mode (rare)
     ctx->n_results = total_out;
     ctx->p_user.need((size_t)total_out); ctx->p_item.need((size_t)total_out); ctx->p_cluster.need((size_t)total_out);
     ctx->p_s64.need((size_t)total_out); ctx->p_s32.need((size_t)total_out);
@@ -682,13 +721,20 @@ static int run_pipeline(fy_rm2_ctx* ctx) {
         if (g.kind == SEG_GRAM) ctx->prof.ms_gram += ms;
         else if (g.kind == SEG_SCORE) ctx->prof.ms_score += ms;
         else if (g.kind == SEG_TOPN) ctx->prof.ms_topn += ms;
+        else if (g.kind == SEG_REFINE) ctx->prof.ms_refine += ms;
     }
     ctx->prof.log_terms = terms;
-    ctx->prof.score_bytes = 8.0 * terms;
+    ctx->prof.score_bytes = ctx->prof.bytes_per_term * terms;
     ctx->prof.users_scored = ctx->users_scored;
     ctx->prof.kernel_launches = ctx->launches;
     ctx->have_results = true;
     return FY_OK;
+}
+
+static int run_pipeline(fy_rm2_ctx* ctx) {
+    int rc = run_pipeline_impl(ctx, false);
+    if (rc == 1) rc = run_pipeline_impl(ctx, true);
+    return rc;
 }
 
 extern "C" int fy_rm2_run(fy_rm2_ctx* ctx) {

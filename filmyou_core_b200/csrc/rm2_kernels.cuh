@@ -35,6 +35,8 @@ enum DevFlag : int {
 constexpr int SCORE_TILE = 256;     // candidates per score CTA (2 per thread)
 constexpr int SCORE_THREADS = 128;
 constexpr int SCORE_CHUNK = 512;    // rated items staged in shared memory at a time
+constexpr int SCOREH_TILE = 512;    // candidates per CTA of the hi-word score kernel (4 per thread)
+constexpr int REFINE_THREADS = 256;
 constexpr int H_SLICE = 512;        // columns of one H row built by one warp (4 KB of doubles)
 constexpr int H_THREADS = 256;
 constexpr int H_WARPS = H_THREADS / 32;   // 8 independent (row, slice) tasks per CTA
@@ -369,6 +371,12 @@ __global__ void k_user_work(const int32_t* __restrict__ rowptr, const int32_t* _
 // every bit of H -- is fixed, and two identical item columns give identical H columns (exact ties
 // stay exact ties, as in the reference's double loop).
 // ---------------------------------------------------------------------------------------------
+// upper 32 bits of a positive double, rounded to nearest on the dropped half: 20 mantissa bits,
+// relative error <= 2^-21.  The hi-word plane of H is what the approximate score kernel streams.
+__device__ __forceinline__ uint32_t hi_word_rn(double x) {
+    return (uint32_t)(((unsigned long long)__double_as_longlong(x) + 0x80000000ull) >> 32);
+}
+
 // first CSR entry of every (user, column slice) of one cluster; slice q covers local item ids
 // [q*slice_w, (q+1)*slice_w); n_bound = number of slices + 1
 __global__ void k_chunk_ptr(int32_t rank0, int32_t K_c, int32_t n_bound, int32_t slice_w,
@@ -396,7 +404,7 @@ k_build_H(int32_t I_c, int32_t ld, int32_t n_slices, int32_t slot0,
           const double* __restrict__ c_b, const double* __restrict__ c_alpha,
           const int32_t* __restrict__ csc_lu, const double* __restrict__ csc_delta,
           const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ csr_loc,
-          const double* __restrict__ csr_delta, double* __restrict__ H) {
+          const double* __restrict__ csr_delta, double* __restrict__ H, uint32_t* __restrict__ Hh) {
     extern __shared__ double acc_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int32_t j = blockIdx.x;
@@ -464,18 +472,25 @@ k_build_H(int32_t I_c, int32_t ld, int32_t n_slices, int32_t slot0,
     const double bj = c_b[slot0 + j];
     double* __restrict__ row = H + (size_t)j * ld + c0;
     const double* __restrict__ al = c_alpha + slot0 + c0;
+    uint32_t* __restrict__ rowh = Hh ? Hh + (size_t)j * ld + c0 : nullptr;
     for (int t = lane * 2; t < w; t += 64) {
         if (t + 1 < w) {
             double2 o;
             o.x = __fma_rn(bj, al[t], acc[t]);
             o.y = __fma_rn(bj, al[t + 1], acc[t + 1]);
             *reinterpret_cast<double2*>(row + t) = o;
+            if (rowh) *reinterpret_cast<uint2*>(rowh + t) = make_uint2(hi_word_rn(o.x), hi_word_rn(o.y));
         } else {
-            row[t] = __fma_rn(bj, al[t], acc[t]);
+            const double o = __fma_rn(bj, al[t], acc[t]);
+            row[t] = o;
+            if (rowh) rowh[t] = hi_word_rn(o);
         }
     }
     if (sl == n_slices - 1)
-        for (int32_t i = I_c + lane; i < ld; i += 32) H[(size_t)j * ld + i] = 1.0;   // padding columns
+        for (int32_t i = I_c + lane; i < ld; i += 32) {                              // padding columns
+            H[(size_t)j * ld + i] = 1.0;
+            if (Hh) Hh[(size_t)j * ld + i] = 0x3ff00000u;
+        }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -601,6 +616,224 @@ k_score(const double* __restrict__ H, int32_t I_c, int32_t ld, int32_t rank_begi
         atomicAdd(st, (unsigned long long)cnt);
         atomicMin(st + 1, kmin);
         atomicMax(st + 2, kmax);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Approximate score kernel: identical to k_score but streams the hi-word plane of H (4 bytes per
+// log-term, 20-bit mantissa): CTA = (user, 512 candidates), 16-byte loads of 4 candidates.
+// |log t~ - log t| <= 2^-21 per term, so |score~ - score| <= n_u * 2^-21 (+ fp64 noise): a rigorous
+// bound that k_margin_gather turns into a candidate set containing the exact top-N; k_refine then
+// re-scores those candidates from the fp64 plane.  Only used when every t > 0 (L >= 2).
+// ---------------------------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(SCORE_THREADS)
+k_score_hi(const uint32_t* __restrict__ Hh, int32_t I_c, int32_t ld, int32_t rank_begin, int32_t slot0,
+           const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_loc,
+           const double* __restrict__ csr_c, const double* __restrict__ c_b,
+           double log_items, double log_K, double* __restrict__ scores, unsigned long long* __restrict__ ustat) {
+    __shared__ int32_t s_j[SCORE_CHUNK];
+    __shared__ double s_c[SCORE_CHUNK];
+    __shared__ unsigned s_rated[SCOREH_TILE / 32];
+
+    const int32_t rank = rank_begin + blockIdx.x;
+    const int32_t tile0 = blockIdx.y * SCOREH_TILE;
+    const int32_t i = tile0 + 4 * threadIdx.x;
+    const int32_t e0 = rowptr[rank];
+    const int32_t n = rowptr[rank + 1] - e0;
+
+    if (threadIdx.x < SCOREH_TILE / 32) s_rated[threadIdx.x] = 0u;
+    double b[4], p[4];
+    int ex[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { b[q] = (i + q < I_c) ? c_b[slot0 + i + q] : 0.0; p[q] = 1.0; ex[q] = 0; }
+    const uint32_t* __restrict__ Hc = Hh + i;
+
+    for (int32_t base = 0; base < n; base += SCORE_CHUNK) {
+        const int32_t cnt = min(SCORE_CHUNK, n - base);
+        __syncthreads();
+        for (int32_t k = threadIdx.x; k < cnt; k += SCORE_THREADS) {
+            const int32_t j = csr_loc[e0 + base + k];
+            s_j[k] = j;
+            s_c[k] = csr_c[e0 + base + k];
+            const int32_t d = j - tile0;
+            if (d >= 0 && d < SCOREH_TILE) atomicOr(&s_rated[d >> 5], 1u << (d & 31));
+        }
+        __syncthreads();
+        int32_t k = 0;
+        for (; k + 8 <= cnt; k += 8) {
+            uint4 h[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) h[q] = __ldg(reinterpret_cast<const uint4*>(Hc + (size_t)s_j[k + q] * ld));
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const double c = s_c[k + q];
+                p[0] *= fma(b[0], c, __hiloint2double((int)h[q].x, 0));
+                p[1] *= fma(b[1], c, __hiloint2double((int)h[q].y, 0));
+                p[2] *= fma(b[2], c, __hiloint2double((int)h[q].z, 0));
+                p[3] *= fma(b[3], c, __hiloint2double((int)h[q].w, 0));
+                if ((q + 1) % L == 0) {
+#pragma unroll
+                    for (int z = 0; z < 4; z++) peel_exponent(p[z], ex[z]);
+                }
+            }
+        }
+        for (; k < cnt; k++) {
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(Hc + (size_t)s_j[k] * ld));
+            const double c = s_c[k];
+            p[0] *= fma(b[0], c, __hiloint2double((int)h.x, 0));
+            p[1] *= fma(b[1], c, __hiloint2double((int)h.y, 0));
+            p[2] *= fma(b[2], c, __hiloint2double((int)h.z, 0));
+            p[3] *= fma(b[3], c, __hiloint2double((int)h.w, 0));
+            if (((k & 7) + 1) % L == 0 || k + 1 == cnt) {
+#pragma unroll
+                for (int z = 0; z < 4; z++) peel_exponent(p[z], ex[z]);
+            }
+        }
+    }
+    __syncthreads();
+    const double pvpi = __dsub_rn(__dmul_rn((double)(n - 1), log_items), __dmul_rn((double)n, log_K));
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double NANV = __longlong_as_double(0x7ff8000000000000ll);
+    double s[4];
+    const int d = 4 * threadIdx.x;
+    const unsigned word = s_rated[d >> 5];
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        s[q] = fma((double)ex[q], LN2_HI, fma((double)ex[q], LN2_LO, log(p[q]))) + pvpi;
+        if (((word >> ((d + q) & 31)) & 1u) || i + q >= I_c) s[q] = NANV;
+        if (s[q] == s[q]) { const unsigned long long k = desc_key(s[q]); kmin = min(kmin, k); kmax = max(kmax, k); cnt++; }
+    }
+    double* dst = scores + (size_t)blockIdx.x * ld + i;
+    *reinterpret_cast<double2*>(dst) = make_double2(s[0], s[1]);
+    *reinterpret_cast<double2*>(dst + 2) = make_double2(s[2], s[3]);
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0) {
+        unsigned long long* st = ustat + 3 * (size_t)blockIdx.x;
+        atomicAdd(st, (unsigned long long)cnt);
+        atomicMin(st + 1, kmin);
+        atomicMax(st + 2, kmax);
+    }
+}
+
+// candidates that can be in the exact top-N: approximate score >= (N-th approximate score) - 2*eps
+__global__ void __launch_bounds__(256)
+k_margin_gather(const double* __restrict__ scores, int32_t I_c, int32_t ld, int32_t rank_begin, int32_t ub,
+                const int32_t* __restrict__ rowptr, int32_t out_stride, const double* __restrict__ out_score,
+                const int32_t* __restrict__ out_count, int32_t cap, int32_t* __restrict__ cand,
+                int32_t* __restrict__ cand_cnt, int* __restrict__ overflow) {
+    __shared__ int s_n;
+    const int32_t rank = rank_begin + blockIdx.x, orow = rank - ub;
+    const int32_t n_out = out_count[orow];
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    if (n_out > 0) {
+        const double n_u = (double)(rowptr[rank + 1] - rowptr[rank]);
+        const double eps = n_u * 4.8e-7 + 1e-9;                    // n_u * 2^-21 * 1.007 + fp64 slack
+        const double thr = out_score[(size_t)orow * out_stride + n_out - 1] - 2.0 * eps;
+        const double* __restrict__ row = scores + (size_t)blockIdx.x * ld;
+        for (int32_t i = threadIdx.x; i < I_c; i += blockDim.x) {
+            const double sc = row[i];
+            if (sc == sc && sc >= thr) {
+                const int pos = atomicAdd(&s_n, 1);
+                if (pos < cap) cand[(size_t)blockIdx.x * cap + pos] = i;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cand_cnt[blockIdx.x] = s_n;
+        if (s_n > cap) atomicAdd(overflow, 1);
+    }
+}
+
+// exact fp64 re-score of the candidates: grid (user, candidate group), one warp per candidate, lanes
+// stride the rated items (4 gathers in flight per lane); the lane products are combined by a fixed
+// butterfly, so the result is deterministic and identical item columns give identical scores.
+__global__ void __launch_bounds__(REFINE_THREADS)
+k_refine_score(const double* __restrict__ H, int32_t ld, int32_t rank_begin, int32_t slot0,
+               const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_loc, const double* __restrict__ csr_c,
+               const double* __restrict__ c_b, double log_items, double log_K,
+               int32_t cap, const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
+               double* __restrict__ cand_score) {
+    const int32_t cnt = cand_cnt[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t q = blockIdx.y * (REFINE_THREADS / 32) + warp;
+    if (cnt > cap || q >= cnt) return;
+    const int32_t rank = rank_begin + blockIdx.x;
+    const int32_t e0 = rowptr[rank], n = rowptr[rank + 1] - e0;
+    const int32_t i = cand[(size_t)blockIdx.x * cap + q];
+    const double bi = c_b[slot0 + i];
+    const double* __restrict__ Hi = H + i;
+    double p = 1.0;
+    int ex = 0;
+    int32_t k = lane;
+    for (; k + 96 < n; k += 128) {
+        double h[4], c[4];
+#pragma unroll
+        for (int z = 0; z < 4; z++) { h[z] = Hi[(size_t)csr_loc[e0 + k + 32 * z] * ld]; c[z] = csr_c[e0 + k + 32 * z]; }
+#pragma unroll
+        for (int z = 0; z < 4; z++) { p *= fma(bi, c[z], h[z]); peel_exponent(p, ex); }
+    }
+    for (; k < n; k += 32) { p *= fma(bi, csr_c[e0 + k], Hi[(size_t)csr_loc[e0 + k] * ld]); peel_exponent(p, ex); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double po = __shfl_xor_sync(0xffffffffu, p, o);
+        const int eo = __shfl_xor_sync(0xffffffffu, ex, o);
+        p *= po; ex += eo;
+        peel_exponent(p, ex);
+    }
+    if (lane == 0) {
+        const double pvpi = __dsub_rn(__dmul_rn((double)(n - 1), log_items), __dmul_rn((double)n, log_K));
+        const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+        cand_score[(size_t)blockIdx.x * cap + q] = fma((double)ex, LN2_HI, fma((double)ex, LN2_LO, log(p))) + pvpi;
+    }
+}
+
+// final (score desc, item id asc) order of the re-scored candidates -> the user's top-N
+__global__ void __launch_bounds__(REFINE_THREADS)
+k_refine_sort(int32_t rank_begin, int32_t ub, int32_t slot0, const int32_t* __restrict__ c_item,
+              int32_t cap, const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
+              const double* __restrict__ cand_score, int32_t out_stride, int32_t* __restrict__ out_item,
+              double* __restrict__ out_score, const int32_t* __restrict__ out_count) {
+    extern __shared__ unsigned char smem_raw[];
+    const int32_t orow = rank_begin + blockIdx.x - ub;
+    const int32_t n_out = out_count[orow];
+    const int32_t cnt = cand_cnt[blockIdx.x];
+    if (n_out == 0 || cnt > cap) return;                           // nothing to do / overflow (run is redone exactly)
+    int P2 = 1; while (P2 < cnt) P2 <<= 1;
+    uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);
+    int32_t* si = reinterpret_cast<int32_t*>(smem_raw + (size_t)P2 * sizeof(uint64_t));
+    const int tid = threadIdx.x;
+    for (int t = tid; t < P2; t += REFINE_THREADS) {
+        if (t < cnt) { sk[t] = desc_key(cand_score[(size_t)blockIdx.x * cap + t]); si[t] = cand[(size_t)blockIdx.x * cap + t]; }
+        else { sk[t] = ~0ull; si[t] = 0x7fffffff; }
+    }
+    __syncthreads();
+    for (int k = 2; k <= P2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < P2; t += REFINE_THREADS) {
+                const int ixj = t ^ j;
+                if (ixj > t) {
+                    const uint64_t ka = sk[t], kb = sk[ixj];
+                    const int32_t ia = si[t], ib = si[ixj];
+                    const bool a_gt_b = (ka > kb) || (ka == kb && ia > ib);
+                    const bool up = ((t & k) == 0);
+                    if (a_gt_b == up) { sk[t] = kb; sk[ixj] = ka; si[t] = ib; si[ixj] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = tid; t < n_out; t += REFINE_THREADS) {
+        out_item[(size_t)orow * out_stride + t] = c_item[slot0 + si[t]];
+        out_score[(size_t)orow * out_stride + t] = key_to_score(sk[t]);
     }
 }
 

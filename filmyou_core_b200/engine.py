@@ -41,14 +41,16 @@ class Rm2Error(RuntimeError):
 class Rm2Params(C.Structure):
     _fields_ = [("lambda_", C.c_double), ("number_of_items", C.c_int32), ("top_n", C.c_int32),
                 ("filter_users", C.c_int32), ("device", C.c_int32), ("shard_rank", C.c_int32),
-                ("shard_count", C.c_int32), ("tie_break", C.c_int32)]
+                ("shard_count", C.c_int32), ("tie_break", C.c_int32), ("score_mode", C.c_int32)]
 
 
 class Rm2Profile(C.Structure):
     _fields_ = [("ms_total", C.c_double), ("ms_index", C.c_double), ("ms_gram", C.c_double),
                 ("ms_score", C.c_double), ("ms_topn", C.c_double), ("log_terms", C.c_double),
                 ("score_bytes", C.c_double), ("gram_bytes", C.c_double), ("users_scored", C.c_int64),
-                ("kernel_launches", C.c_int64), ("clusters_touched", C.c_int32), ("score_launches", C.c_int32)]
+                ("kernel_launches", C.c_int64), ("clusters_touched", C.c_int32), ("score_launches", C.c_int32),
+                ("ms_refine", C.c_double), ("bytes_per_term", C.c_double), ("exact_rerun", C.c_int32),
+                ("reserved", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -136,13 +138,14 @@ class Rm2Engine:
     """One context = one GPU.  Thin, 1:1 over the C ABI."""
 
     def __init__(self, lam=0.1, number_of_items=0, top_n=1000, filter_users=0, device=0,
-                 shard_rank=0, shard_count=1):
+                 shard_rank=0, shard_count=1, score_mode=0):
         self._L = load_library()
         self._h = C.c_void_p()
         p = Rm2Params()
         self._L.fy_rm2_default_params(C.byref(p))
         p.lambda_, p.number_of_items, p.top_n, p.filter_users = float(lam), int(number_of_items), int(top_n), int(filter_users)
         p.device, p.shard_rank, p.shard_count = int(device), int(shard_rank), int(shard_count)
+        p.score_mode = int(score_mode)
         rc = self._L.fy_rm2_create(C.byref(self._h), C.byref(p))
         if rc != 0:
             self._h = C.c_void_p()

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define FY_RM2_ABI_VERSION 1
+#define FY_RM2_ABI_VERSION 2
 
 typedef enum fy_status {
     FY_OK = 0,
@@ -72,6 +72,9 @@ typedef struct fy_rm2_params {
     int32_t shard_rank;        /* this context scores shard `shard_rank` of `shard_count`          */
     int32_t shard_count;       /*   (users partitioned by estimated work; 0/1 = everything)        */
     int32_t tie_break;         /* 0 = canonical (score desc, item id asc); nothing else defined    */
+    int32_t score_mode;        /* 0 = auto: stream the 4-byte hi-word plane of H, then re-score the */
+                               /*     provably sufficient candidate set exactly in fp64;            */
+                               /* 1 = exact: stream the fp64 plane for every term                   */
 } fy_rm2_params;
 
 typedef struct fy_rm2_ctx fy_rm2_ctx;
@@ -142,6 +145,10 @@ typedef struct fy_rm2_profile {
     int64_t kernel_launches; /* launches of this library's own kernels inside fy_rm2_run         */
     int32_t clusters_touched;
     int32_t score_launches;
+    double ms_refine;       /* margin gather + exact fp64 re-score of the candidates (auto mode) */
+    double bytes_per_term;  /* 4 (hi-word plane) or 8 (fp64 plane): what score_bytes counts      */
+    int32_t exact_rerun;    /* 1 if a candidate list overflowed and the run was redone in exact mode */
+    int32_t reserved;
 } fy_rm2_profile;
 int fy_rm2_get_profile(const fy_rm2_ctx* ctx, fy_rm2_profile* out);
 

@@ -26,7 +26,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     L = fy.load_library()
     for name in _declared():
         assert hasattr(L, name), name
-    assert L.fy_rm2_abi_version() == 1
+    assert L.fy_rm2_abi_version() == 2
 
 
 def test_default_params_match_the_reference_defaults():

@@ -59,11 +59,14 @@ def test_golden_exact_tie(golden_ratings):
     assert scores[k38] == scores[k43] and k43 == k38 + 1
 
 
+@pytest.mark.parametrize("score_mode", [0, 1])
 @pytest.mark.parametrize("shape,lam,top_n", [("tiny", 0.1, 10), ("small", 0.1, 100), ("small", 0.9, 7),
                                               ("ml-100k", 0.1, 100)])
-def test_synthetic_vs_oracle(shape, lam, top_n):
+def test_synthetic_vs_oracle(shape, lam, top_n, score_mode):
+    # score_mode 0 = hi-word stream + exact fp64 re-score of the candidate set; 1 = fp64 stream
     r = datagen.generate(shape)
-    got = gpu_run(r, lam, r.n_items, top_n)
+    got = gpu_run(r, lam, r.n_items, top_n, score_mode=score_mode)
+    assert got["profile"]["bytes_per_term"] == (4.0 if score_mode == 0 else 8.0)
     want = cpu_run(r, lam, r.n_items, top_n)
     worst = assert_parity(got, want, REL, shape)
     assert worst < 1e-9          # the engine is fp64 end to end; 1e-6 is the contract, this is the margin
@@ -85,6 +88,27 @@ def test_ml1m_sampled_users_vs_oracle():
                               for u in by_user(want)]) for k in ("user", "item", "score64")}
     assert_parity(sub, want, REL, "ml-1m sample")
     assert got["users_scored"] == r.n_users
+
+
+def test_candidate_overflow_falls_back_to_the_exact_stream():
+    # 600 items that nobody else rated identically: every user sees hundreds of candidates with
+    # (near-)identical scores, far more than the candidate capacity for N=5 -> the run must notice
+    # and redo itself in exact mode, with the same answer as score_mode=1
+    rng = np.random.default_rng(3)
+    users = np.arange(1, 41)
+    user, item, score = [], [], []
+    for u in users:                               # everybody rates items 1..5, nobody rates 6..605 twice
+        for i in range(1, 6):
+            user.append(u); item.append(i); score.append(float(rng.integers(1, 6)))
+    for i in range(6, 606):                       # each cold item rated once, all by user 1, same score
+        user.append(1); item.append(i); score.append(3.0)
+    r = datagen.Ratings("ovf", 40, 605, np.array(user, np.int32), np.array(item, np.int32), np.array(score, np.float32),
+                        users.astype(np.int32), np.zeros(40, np.int32), np.array([40], np.int32), 0)
+    a = gpu_run(r, 0.1, 605, 5, score_mode=0)
+    b = gpu_run(r, 0.1, 605, 5, score_mode=1)
+    assert a["profile"]["exact_rerun"] == 1 and b["profile"]["exact_rerun"] == 0
+    assert all(np.array_equal(a[k], b[k]) for k in ("user", "item", "score64"))
+    assert_parity(a, cpu_run(r, 0.1, 605, 5), REL, "overflow")
 
 
 def test_lambda_edge_cases():
