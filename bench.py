@@ -33,6 +33,16 @@ LAMBDA = 0.1          # reference default, M/rmrecommender/RMRecommenderDriver.j
 TOP_N = 100           # BASELINE.json configs: "RM2 top-100"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    ncu --set full capture (profiles/r01_ncu_traffic.json); None when no capture exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            return float(json.load(f)[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -167,13 +177,35 @@ def run_reference_arm(args, r, workload):
             "config": workload, "cpu_baseline": last,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU restatement of the reference (no JVM in this image); ms_per_step = extrapolated whole job"}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Library chatter (e.g. NCCL's version banner, printed with printf) must not share stdout with the
+    ONE JSON line: point fd 1 at stderr and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(line, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -210,7 +242,6 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("FY_NCCL_DEBUG", "WARN")   # keep stdout to the ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
@@ -256,7 +287,9 @@ def main():
     sums = torch.tensor([sum(p["ms_score"] for p in profs), sum(p["score_bytes"] for p in profs),
                          sum(p["ms_gram"] for p in profs), sum(p["ms_index"] for p in profs),
                          sum(p["ms_topn"] for p in profs), float(launches),
-                         float(sum(p["score_launches"] for p in profs))], dtype=torch.float64, device=dev)
+                         float(sum(p["score_launches"] for p in profs)), sum(p["ms_refine"] for p in profs),
+                         float(profs[-1]["bytes_per_term"]), float(sum(p["exact_rerun"] for p in profs))],
+                        dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(scored, op=dist.ReduceOp.SUM)
@@ -319,16 +352,23 @@ def main():
     for s in all_sums:
         s = s.tolist()
         per_rank.append({"ms_score": s[0], "score_bytes": s[1], "ms_gram": s[2], "ms_index": s[3], "ms_topn": s[4],
-                         "launches": s[5], "score_launches": s[6]})
+                         "launches": s[5], "score_launches": s[6], "ms_refine": s[7], "bytes_per_term": s[8],
+                         "exact_rerun": s[9]})
     worst = max(per_rank, key=lambda x: x["ms_score"])
     achieved = worst["score_bytes"] / (worst["ms_score"] * 1e-3) / 1e9 if worst["ms_score"] > 0 else 0.0
-    roofline = {"kernel": "fy::k_score", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    hi = worst["bytes_per_term"] == 4.0
+    roofline = {"kernel": "fy::k_score_hi" if hi else "fy::k_score", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("k_score_hi" if hi else "k_score"),
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": worst["score_bytes"] / max(worst["score_launches"], 1),
                 "avg_launch_ms": worst["ms_score"] / max(worst["score_launches"], 1),
-                "definition": "8 B per (user, candidate, rated item) log-term = one fp64 element of H streamed; "
-                              "sum over launches / sum of launch durations (CUDA events on the launching stream)",
-                "stage_ms_per_step": {k: worst[k] / args.steps for k in ("ms_index", "ms_gram", "ms_score", "ms_topn")}}
+                "definition": "%d B per (user, candidate, rated item) log-term = one %s element of H streamed; "
+                              "sum over launches / sum of launch durations (CUDA events on the launching stream); "
+                              "frac > 1 = rows re-used out of L2 (traffic = DRAM bytes per launch from the ncu capture "
+                              "of one ML-20M-sized cluster, profiles/)" % (4 if hi else 8, "hi-word (4-byte)" if hi else "fp64"),
+                "stage_ms_per_step": {k: worst[k] / args.steps for k in ("ms_index", "ms_gram", "ms_score", "ms_topn", "ms_refine")},
+                "stages_overlap": "H build, score and top-N/refine run on three streams; stage times are per stream and overlap",
+                "exact_reruns": worst["exact_rerun"]}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload, "clocks": clocks, "e2e": e2e,
@@ -336,7 +376,7 @@ def main():
             "users_scored": users, "datagen_s": t_gen}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(r)
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -84,6 +84,8 @@ struct fy_rm2_ctx {
     DBuf<int32_t> src_a, csc_src, rowptr;
     DBuf<unsigned char> cub_tmp;
     DBuf<double> usum, isum, iprob, bvec, total, work, work_scan, tsum;
+    DBuf<int32_t> n_u;
+    DBuf<float> c_score;
     DBuf<unsigned long long> ustat[2];
     bool exact_scores = false;
     DBuf<unsigned long long> counters;   // [0] n_valid, [1] truncated counter, [2] bits of the smallest positive b_i
@@ -372,60 +374,131 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
 
     // ---------------- index: sort #1 (user rank, item) -> CSR ----------------
     ctx->keys_a.need((size_t)nnz); ctx->keys_b.need((size_t)nnz); ctx->s_score.need((size_t)nnz);
-    ctx->counters.need(3); ctx->flags.need(DF_COUNT);
-    CK(cudaMemsetAsync(ctx->counters.p, 0, 2 * sizeof(unsigned long long), st));
+    ctx->counters.need(4); ctx->flags.need(DF_COUNT);
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(ctx->counters.p + 2, 0xff, sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(ctx->flags.p, 0, sizeof(int) * DF_COUNT, st));
+    const size_t tab = (size_t)KC * TI;
+    ctx->rowptr.need((size_t)U + 1);
+    ctx->usum.need(U);
+    ctx->isum.need(TI); ctx->iprob.need(TI); ctx->bvec.need(TI); ctx->total.need(1);
+    ctx->icount.need(KC); ctx->item_off.need((size_t)KC + 1);
+    ctx->tstart.need(tab);
     LAUNCH(ctx, k_make_keys, cdiv(nnz, 256), 256, 0, ctx->in_user.p, ctx->in_item.p, ctx->in_score.p, nnz,
            ctx->uid_sorted.p, ctx->uid_rank.p, U, item_bits, ctx->max_item, ctx->keys_a.p, ctx->counters.p, ctx->flags.p);
-    {
+    unsigned long long h_counters[2]; int h_flags[DF_COUNT];
+    // Sharded index: with exact (dyadic) scores the global statistics need no sort, so each rank sorts and
+    // indexes only the ratings of the clusters it touches (~1/N of them) instead of all of them.
+    const bool sharded_index = ctx->prm.shard_count > 1 && ctx->exact_scores && !ctx->use_ext;
+    int32_t ub = 0, ue = U;
+    std::vector<int32_t> h_icount_global((size_t)KC, 0);
+    uint64_t* k_sorted = ctx->keys_b.p;       // (rank, item)-sorted CSR keys
+    uint64_t* k_scratch = ctx->keys_a.p;
+    int32_t m = 0;
+    if (sharded_index) {
+        ctx->n_u.need(U); ctx->work.need(U); ctx->work_scan.need(U); ctx->c_score.need((size_t)nnz);
+        CK(cudaMemsetAsync(ctx->usum.p, 0, (size_t)U * 8, st));
+        CK(cudaMemsetAsync(ctx->n_u.p, 0, (size_t)U * 4, st));
+        CK(cudaMemsetAsync(ctx->isum.p, 0, (size_t)TI * 8, st));
+        CK(cudaMemsetAsync(ctx->tstart.p, 0xff, tab * 4, st));
+        LAUNCH(ctx, k_global_stats, cdiv(nnz, 256), 256, 0, ctx->keys_a.p, ctx->in_score.p, nnz, item_bits, ctx->rank_cluster.p,
+               TI, ctx->usum.p, ctx->n_u.p, ctx->isum.p, ctx->tstart.p);
+        LAUNCH(ctx, k_total_from_usum, cdiv(U, 256), 256, 0, ctx->usum.p, ctx->n_u.p, U, ctx->counters.p + 1, ctx->flags.p);
+        LAUNCH(ctx, k_cluster_item_count, KC, 256, 0, ctx->tstart.p, TI, ctx->icount.p);
+        LAUNCH(ctx, k_user_work_n, cdiv(U, 256), 256, 0, ctx->n_u.p, ctx->rank_cluster.p, ctx->icount.p, U, ctx->work.p);
+        {
+            size_t tmp = 0;
+            CK(cub::DeviceScan::InclusiveSum(nullptr, tmp, ctx->work.p, ctx->work_scan.p, U, st));
+            ctx->cub_tmp.need(tmp);
+            CK(cub::DeviceScan::InclusiveSum(ctx->cub_tmp.p, tmp, ctx->work.p, ctx->work_scan.p, U, st));
+        }
+        // sync A1: input errors, global item counts, work prefix -> this rank's user range
+        std::vector<double> h_scan((size_t)U);
+        CK(cudaMemcpyAsync(h_counters, ctx->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_flags, ctx->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_icount_global.data(), ctx->icount.p, (size_t)KC * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_scan.data(), ctx->work_scan.p, (size_t)U * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        { int rc = check_flags(ctx, h_flags); if (rc != FY_OK) return rc; }
+        if (h_counters[0] == 0) return ctx->fail(FY_E_ARG, "no positive rating");
+        const double tot = h_scan[U - 1];
+        auto bound = [&](int r) -> int32_t {
+            if (r <= 0) return 0;
+            if (r >= ctx->prm.shard_count) return U;
+            const double target = tot * (double)r / (double)ctx->prm.shard_count;
+            return (int32_t)(std::lower_bound(h_scan.begin(), h_scan.end(), target) - h_scan.begin());
+        };
+        ub = bound(ctx->prm.shard_rank);
+        ue = bound(ctx->prm.shard_rank + 1);
+        int32_t rl = 0, rh = 0;                                 // rank range of the touched clusters
+        if (ue > ub) {
+            rl = ctx->h_cstart[ctx->h_rank_cluster[ub]];
+            rh = ctx->h_cstart[ctx->h_rank_cluster[ue - 1] + 1];
+        }
+        LAUNCH(ctx, k_compact_local, cdiv(nnz, 256), 256, 0, ctx->keys_a.p, ctx->in_score.p, nnz, item_bits, rl, rh,
+               ctx->keys_b.p, ctx->c_score.p, ctx->counters.p + 3);
+        unsigned long long h_m = 0;
+        CK(cudaMemcpyAsync(&h_m, ctx->counters.p + 3, sizeof(h_m), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));                          // sync A2: number of local ratings
+        m = (int32_t)h_m;
+        if (m > 0) {
+            size_t tmp = 0;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->keys_b.p, ctx->keys_a.p, ctx->c_score.p, ctx->s_score.p,
+                                               (int64_t)m, 0, key_bits, st));
+            ctx->cub_tmp.need(tmp);
+            CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, ctx->keys_b.p, ctx->keys_a.p, ctx->c_score.p, ctx->s_score.p,
+                                               (int64_t)m, 0, key_bits, st));
+        }
+        k_sorted = ctx->keys_a.p; k_scratch = ctx->keys_b.p;
+    } else {
         size_t tmp = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->keys_a.p, ctx->keys_b.p, ctx->in_score.p, ctx->s_score.p,
                                            (int64_t)nnz, 0, key_bits, st));
         ctx->cub_tmp.need(tmp);
         CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, ctx->keys_a.p, ctx->keys_b.p, ctx->in_score.p, ctx->s_score.p,
                                            (int64_t)nnz, 0, key_bits, st));
+        // sync A: number of positive ratings, input errors
+        CK(cudaMemcpyAsync(h_counters, ctx->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_flags, ctx->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        { int rc = check_flags(ctx, h_flags); if (rc != FY_OK) return rc; }
+        m = (int32_t)h_counters[0];
+        if (m <= 0) return ctx->fail(FY_E_ARG, "no positive rating");
     }
-    // sync A: number of positive ratings, input errors
-    unsigned long long h_counters[2]; int h_flags[DF_COUNT];
-    CK(cudaMemcpyAsync(h_counters, ctx->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_flags, ctx->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    { int rc = check_flags(ctx, h_flags); if (rc != FY_OK) return rc; }
-    const int32_t m = (int32_t)h_counters[0];
     ctx->m = m;
-    if (m <= 0) return ctx->fail(FY_E_ARG, "no positive rating");
-    const uint64_t* keys = ctx->keys_b.p;                    // sorted (rank, item)
+    const uint64_t* keys = k_sorted;                          // sorted (rank, item)
+    const int32_t m1 = std::max(m, 1);
 
-    ctx->rowptr.need((size_t)U + 1);
-    ctx->usum.need(U);
-    LAUNCH(ctx, k_rows, cdiv(m, 256), 256, 0, keys, m, item_bits, U, ctx->rowptr.p, ctx->flags.p);
-    LAUNCH(ctx, k_user_sum, cdiv(U, 128), 128, 0, ctx->rowptr.p, ctx->s_score.p, U,
-           ctx->use_ext ? ctx->ext_usum.p : (const double*)nullptr, ctx->usum.p, ctx->counters.p + 1, ctx->flags.p);
+    CK(cudaMemsetAsync(ctx->rowptr.p, 0xff, ((size_t)U + 1) * 4, st));
+    if (m > 0) LAUNCH(ctx, k_rows, cdiv(m, 256), 256, 0, keys, m, item_bits, U, ctx->rowptr.p, ctx->flags.p);
+    LAUNCH(ctx, k_rows_gap, cdiv(U + 1, 256), 256, 0, keys, m, item_bits, U, ctx->rowptr.p);
+    if (!sharded_index)
+        LAUNCH(ctx, k_user_sum, cdiv(U, 128), 128, 0, ctx->rowptr.p, ctx->s_score.p, U,
+               ctx->use_ext ? ctx->ext_usum.p : (const double*)nullptr, ctx->usum.p, ctx->counters.p + 1, ctx->flags.p);
 
     // ---------------- sort #2 (item, user rank) -> CSC ----------------
-    ctx->src_a.need(m); ctx->csc_src.need(m); ctx->keys_c.need(m);
-    LAUNCH(ctx, k_make_keys2, cdiv(m, 256), 256, 0, keys, m, item_bits, rank_bits, ctx->keys_a.p, ctx->src_a.p);
-    {
+    ctx->src_a.need(m1); ctx->csc_src.need(m1); ctx->keys_c.need(m1);
+    if (m > 0) {
+        LAUNCH(ctx, k_make_keys2, cdiv(m, 256), 256, 0, keys, m, item_bits, rank_bits, k_scratch, ctx->src_a.p);
         size_t tmp = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->keys_a.p, ctx->keys_c.p, ctx->src_a.p, ctx->csc_src.p,
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_scratch, ctx->keys_c.p, ctx->src_a.p, ctx->csc_src.p,
                                            (int64_t)m, 0, std::min(64, item_bits + rank_bits), st));
         ctx->cub_tmp.need(tmp);
-        CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, ctx->keys_a.p, ctx->keys_c.p, ctx->src_a.p, ctx->csc_src.p,
+        CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, k_scratch, ctx->keys_c.p, ctx->src_a.p, ctx->csc_src.p,
                                            (int64_t)m, 0, std::min(64, item_bits + rank_bits), st));
     }
     const uint64_t* keys2 = ctx->keys_c.p;                   // sorted (item, rank)
 
-    const size_t tab = (size_t)KC * TI;
-    ctx->ifirst.need(TI); ctx->ilast.need(TI); ctx->tstart.need(tab); ctx->tend.need(tab); ctx->tloc.need(tab);
-    ctx->isum.need(TI); ctx->iprob.need(TI); ctx->bvec.need(TI); ctx->total.need(1);
-    ctx->icount.need(KC); ctx->item_off.need((size_t)KC + 1);
+    ctx->ifirst.need(TI); ctx->ilast.need(TI); ctx->tend.need(tab); ctx->tloc.need(tab);
     CK(cudaMemsetAsync(ctx->ifirst.p, 0, (size_t)TI * 4, st));
     CK(cudaMemsetAsync(ctx->ilast.p, 0, (size_t)TI * 4, st));
     CK(cudaMemsetAsync(ctx->tstart.p, 0xff, tab * 4, st));
-    LAUNCH(ctx, k_item_groups, cdiv(m, 256), 256, 0, keys2, m, rank_bits, ctx->rank_cluster.p, TI,
-           ctx->ifirst.p, ctx->ilast.p, ctx->tstart.p, ctx->tend.p);
-    if (ctx->exact_scores && !ctx->use_ext) {
+    if (m > 0) LAUNCH(ctx, k_item_groups, cdiv(m, 256), 256, 0, keys2, m, rank_bits, ctx->rank_cluster.p, TI,
+                      ctx->ifirst.p, ctx->ilast.p, ctx->tstart.p, ctx->tend.p);
+    if (sharded_index) {
+        LAUNCH(ctx, k_item_prob_isum, cdiv(TI, 128), 128, 0, ctx->isum.p, TI, ctx->counters.p + 1, lambda,
+               ctx->iprob.p, ctx->bvec.p, ctx->total.p, ctx->counters.p + 2);
+    } else if (ctx->exact_scores && !ctx->use_ext) {
         ctx->tsum.need(tab);
         LAUNCH(ctx, k_group_sum, cdiv((int64_t)tab, 256), 256, 0, ctx->tstart.p, ctx->tend.p, ctx->csc_src.p, ctx->s_score.p, tab, ctx->tsum.p);
         LAUNCH(ctx, k_item_prob_fast, cdiv(TI, 128), 128, 0, ctx->tsum.p, KC, TI, ctx->counters.p + 1, lambda,
@@ -438,10 +511,10 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     LAUNCH(ctx, k_cluster_item_count, KC, 256, 0, ctx->tstart.p, TI, ctx->icount.p);
     LAUNCH(ctx, k_cluster_offsets, 1, 32, 0, ctx->icount.p, KC, ctx->item_off.p);
 
-    // per-user work for sharding
+    // per-user work for sharding (replicated-index path; the sharded index did this before compacting)
     ctx->work.need(U); ctx->work_scan.need(U);
-    LAUNCH(ctx, k_user_work, cdiv(U, 256), 256, 0, ctx->rowptr.p, ctx->rank_cluster.p, ctx->icount.p, U, ctx->work.p);
-    if (ctx->prm.shard_count > 1) {
+    if (!sharded_index) LAUNCH(ctx, k_user_work, cdiv(U, 256), 256, 0, ctx->rowptr.p, ctx->rank_cluster.p, ctx->icount.p, U, ctx->work.p);
+    if (ctx->prm.shard_count > 1 && !sharded_index) {
         size_t tmp = 0;
         CK(cub::DeviceScan::InclusiveSum(nullptr, tmp, ctx->work.p, ctx->work_scan.p, U, st));
         ctx->cub_tmp.need(tmp);
@@ -457,7 +530,7 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     unsigned long long h_bmin_bits = 0;
     CK(cudaMemcpyAsync(&h_bmin_bits, ctx->counters.p + 2, sizeof(h_bmin_bits), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_flags, ctx->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
-    if (ctx->prm.shard_count > 1) {
+    if (ctx->prm.shard_count > 1 && !sharded_index) {
         h_scan.resize(U);
         CK(cudaMemcpyAsync(h_scan.data(), ctx->work_scan.p, (size_t)U * 8, cudaMemcpyDeviceToHost, st));
     }
@@ -466,8 +539,8 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     const int32_t n_slots = ctx->h_item_off[KC];
 
     // shard = contiguous range of user ranks with ~equal estimated work (n_u * I_c)
-    int32_t ub = 0, ue = U;
-    if (ctx->prm.shard_count > 1) {
+    if (!sharded_index) for (int32_t c = 0; c < KC; c++) h_icount_global[c] = ctx->h_icount[c];
+    if (ctx->prm.shard_count > 1 && !sharded_index) {
         const double tot = h_scan[U - 1];
         auto bound = [&](int r) -> int32_t {
             if (r <= 0) return 0;
@@ -481,17 +554,21 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     ctx->shard_begin = ub; ctx->shard_end = ue;
 
     // ---------------- local item numbering, d, alpha, c(u,j) ----------------
-    ctx->c_item.need(n_slots); ctx->c_start.need(n_slots); ctx->c_len.need(n_slots);
-    ctx->c_b.need(n_slots); ctx->c_alpha.need(n_slots);
-    ctx->csr_loc.need(m); ctx->csr_delta.need(m); ctx->csr_c.need(m); ctx->csc_lu.need(m); ctx->csc_delta.need(m);
+    const int32_t ns1 = std::max(n_slots, 1);
+    ctx->c_item.need(ns1); ctx->c_start.need(ns1); ctx->c_len.need(ns1);
+    ctx->c_b.need(ns1); ctx->c_alpha.need(ns1);
+    ctx->csr_loc.need(m1); ctx->csr_delta.need(m1); ctx->csr_c.need(m1); ctx->csc_lu.need(m1); ctx->csc_delta.need(m1);
     LAUNCH(ctx, k_local_items, KC, 1024, 0, ctx->tstart.p, ctx->tend.p, TI, ctx->item_off.p, ctx->bvec.p,
            ctx->tloc.p, ctx->c_item.p, ctx->c_start.p, ctx->c_len.p, ctx->c_b.p);
-    LAUNCH(ctx, k_delta, cdiv(m, 256), 256, 0, keys, ctx->s_score.p, m, item_bits, ctx->rank_cluster.p, ctx->usum.p,
-           ctx->bvec.p, ctx->tloc.p, TI, lambda, ctx->csr_loc.p, ctx->csr_delta.p);
-    LAUNCH(ctx, k_csc_fill, cdiv(m, 256), 256, 0, keys2, ctx->csc_src.p, m, rank_bits, ctx->rank_cluster.p, ctx->cstart.p,
-           ctx->csr_delta.p, ctx->csc_lu.p, ctx->csc_delta.p);
-    LAUNCH(ctx, k_alpha_cuj, cdiv(n_slots, 128), 128, 0, ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, keys2, rank_bits,
-           ctx->rank_cluster.p, ctx->cstart.p, ctx->csc_src.p, ctx->csc_delta.p, n_slots, ctx->c_alpha.p, ctx->csr_c.p);
+    if (m > 0) {
+        LAUNCH(ctx, k_delta, cdiv(m, 256), 256, 0, keys, ctx->s_score.p, m, item_bits, ctx->rank_cluster.p, ctx->usum.p,
+               ctx->bvec.p, ctx->tloc.p, TI, lambda, ctx->csr_loc.p, ctx->csr_delta.p);
+        LAUNCH(ctx, k_csc_fill, cdiv(m, 256), 256, 0, keys2, ctx->csc_src.p, m, rank_bits, ctx->rank_cluster.p, ctx->cstart.p,
+               ctx->csr_delta.p, ctx->csc_lu.p, ctx->csc_delta.p);
+    }
+    if (n_slots > 0)
+        LAUNCH(ctx, k_alpha_cuj, cdiv((int64_t)n_slots * 32, 256), 256, 0, ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, keys2, rank_bits,
+               ctx->rank_cluster.p, ctx->cstart.p, ctx->csc_src.p, ctx->csc_delta.p, n_slots, ctx->c_alpha.p, ctx->csr_c.p);
     CK(cudaEventRecord(ev_index, st));
 
     // ---------------- exponent-peel period L from a lower bound on t ----------------
@@ -512,7 +589,7 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     // ---------------- per-cluster scoring ----------------
     const int32_t n_rows = ue - ub;
     int32_t max_ic = 0;
-    for (int32_t c = 0; c < KC; c++) max_ic = std::max(max_ic, ctx->h_icount[c]);
+    for (int32_t c = 0; c < KC; c++) max_ic = std::max(max_ic, h_icount_global[c]);   // same stride on every rank
     const int32_t out_stride = std::max(1, std::min(ctx->prm.top_n, max_ic));
     if (out_stride > TOPN_MAX_SELECT)
         return ctx->fail(FY_E_UNSUPPORTED, "min(numberOfRecommendations, items per cluster) = %d exceeds %d", out_stride, TOPN_MAX_SELECT);

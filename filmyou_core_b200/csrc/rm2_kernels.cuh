@@ -101,6 +101,79 @@ __global__ void k_scan_ratings(const int32_t* __restrict__ r_item, const float* 
     if ((threadIdx.x & 31) == 0 && local_max >= 0) atomicMax(max_item, local_max);
 }
 
+// ---- sharded index (shard_count > 1, exact-score inputs): global statistics without a sort, then only
+// the ratings of the clusters this rank touches are compacted, sorted and indexed ----
+__global__ void k_global_stats(const uint64_t* __restrict__ keys, const float* __restrict__ score, int64_t nnz,
+                               int item_bits, const int32_t* __restrict__ rank_cluster, int32_t table_items,
+                               double* __restrict__ usum, int32_t* __restrict__ n_u, double* __restrict__ isum,
+                               int32_t* __restrict__ present) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const uint64_t k = keys[e];
+    if (k == ~0ull) return;
+    const int32_t rank = (int32_t)(k >> item_bits);
+    const int32_t item = (int32_t)(k & ((1ull << item_bits) - 1));
+    const double s = (double)score[e];
+    atomicAdd(&usum[rank], s);          // exact for dyadic scores, hence order-independent (DF_INEXACT_SCORES clear)
+    atomicAdd(&isum[item], s);
+    atomicAdd(&n_u[rank], 1);
+    present[(size_t)rank_cluster[rank] * table_items + item] = 0;      // table pre-set to -1
+}
+
+__global__ void k_total_from_usum(const double* __restrict__ usum, const int32_t* __restrict__ n_u, int32_t n_users,
+                                  unsigned long long* __restrict__ counter, int* __restrict__ flags) {
+    const int32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_users) return;
+    if (n_u[u] == 0) { atomicOr(&flags[DF_USER_WITHOUT_RATING], 1); return; }
+    atomicAdd(counter, (unsigned long long)((long long)usum[u]) * 100ull);   // DoubleSumAndCountReducer.java:41
+}
+
+__global__ void k_user_work_n(const int32_t* __restrict__ n_u, const int32_t* __restrict__ rank_cluster,
+                              const int32_t* __restrict__ icount, int32_t n_users, double* __restrict__ work) {
+    const int32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_users) return;
+    work[u] = (double)n_u[u] * (double)icount[rank_cluster[u]];
+}
+
+__global__ void k_item_prob_isum(const double* __restrict__ isum, int32_t table_items,
+                                 const unsigned long long* __restrict__ counter, double lambda,
+                                 double* __restrict__ iprob, double* __restrict__ bvec,
+                                 double* __restrict__ total_out, unsigned long long* __restrict__ bmin_bits) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double total = __ddiv_rn((double)(long long)(*counter), 100.0);
+    if (i == 0) *total_out = total;
+    if (i >= table_items) return;
+    const double s = isum[i];
+    const double p = (s > 0.0) ? __ddiv_rn(s, total) : 0.0;
+    const double b = __dmul_rn(lambda, p);
+    iprob[i] = p; bvec[i] = b;
+    if (s > 0.0) atomicMin(bmin_bits, (unsigned long long)__double_as_longlong(b > 0.0 ? b : 0.0));
+}
+
+// keep the ratings whose user rank lies in [rl, rh) (the clusters this rank touches); warp-aggregated append
+__global__ void k_compact_local(const uint64_t* __restrict__ keys, const float* __restrict__ score, int64_t nnz,
+                                int item_bits, int32_t rl, int32_t rh, uint64_t* __restrict__ keys_out,
+                                float* __restrict__ score_out, unsigned long long* __restrict__ counter) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    uint64_t k = 0;
+    if (e < nnz) {
+        k = keys[e];
+        if (k != ~0ull) { const int32_t rank = (int32_t)(k >> item_bits); keep = (rank >= rl && rank < rh); }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (bal == 0u) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == (__ffs(bal) - 1)) base = atomicAdd(counter, (unsigned long long)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+    if (keep) {
+        const unsigned long long pos = base + (unsigned long long)__popc(bal & ((1u << lane) - 1));
+        keys_out[pos] = k;
+        score_out[pos] = score[e];
+    }
+}
+
 // sorted keys -> CSR row pointers over user ranks (+ duplicate detection)
 __global__ void k_rows(const uint64_t* __restrict__ keys, int32_t m, int item_bits, int32_t n_users,
                        int32_t* __restrict__ rowptr, int* __restrict__ flags) {
@@ -114,9 +187,25 @@ __global__ void k_rows(const uint64_t* __restrict__ keys, int32_t m, int item_bi
         prev = (int32_t)(kp >> item_bits);
         if (kp == k) atomicOr(&flags[DF_DUPLICATE], 1);
     }
-    for (int32_t q = prev + 1; q <= r; q++) rowptr[q] = e;
-    if (e == m - 1)
-        for (int32_t q = r + 1; q <= n_users; q++) rowptr[q] = m;
+    if (r - prev <= 64) {
+        for (int32_t q = prev + 1; q <= r; q++) rowptr[q] = e;
+    } else {
+        // long gap (ranks of other shards): leave it to k_rows_gap, which fills it in parallel
+        rowptr[r] = e;
+    }
+}
+
+// fills the rank gaps k_rows skipped: every rank whose rowptr is still "unset" (-1) takes the value of
+// the next set entry (rowptr[n_users] = m is set by the host memset + this kernel's boundary rule)
+__global__ void k_rows_gap(const uint64_t* __restrict__ keys, int32_t m, int item_bits, int32_t n_users,
+                           int32_t* __restrict__ rowptr) {
+    const int32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > n_users) return;
+    if (rowptr[q] >= 0) return;
+    // lower_bound of rank q in the sorted keys
+    int32_t a = 0, b = m;
+    while (a < b) { const int32_t mid = (a + b) >> 1; if ((int32_t)(keys[mid] >> item_bits) < q) a = mid + 1; else b = mid; }
+    rowptr[q] = a;
 }
 
 // RM2-1: user sums in ascending item order (M/rm/DoubleSumReducer.java:31-42) and the truncated
@@ -329,30 +418,48 @@ __global__ void k_csc_fill(const uint64_t* __restrict__ keys2, const int32_t* __
     csc_delta[x] = csr_delta[csc_src[x]];
 }
 
-// alpha_j = sum of d over the raters of j (ascending user), and for every rater u of j
+// alpha_j = sum of d over the raters of j, and for every rater u of j
 //   c(u,j) = (K-1)*b_j + sum_{v != u, v rated j} d_vj = (K-1)*b_j + (prefix before u + suffix after u)
-// one thread per (cluster, item) slot; all terms non-negative, so no cancellation for any lambda.
+// one warp per (cluster, item) slot, 32 raters per step with a shuffle scan and a running carry (fixed
+// order, so deterministic); all terms non-negative, so no cancellation for any lambda.
 __global__ void k_alpha_cuj(const int32_t* __restrict__ c_start, const int32_t* __restrict__ c_len,
                             const double* __restrict__ c_b, const uint64_t* __restrict__ keys2, int rank_bits,
                             const int32_t* __restrict__ rank_cluster, const int32_t* __restrict__ cstart,
                             const int32_t* __restrict__ csc_src, const double* __restrict__ csc_delta,
                             int32_t n_slots, double* __restrict__ c_alpha, double* __restrict__ csr_c) {
-    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t s = (int32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
     if (s >= n_slots) return;
     const int32_t x0 = c_start[s], n = c_len[s];
     const int32_t c = rank_cluster[(int32_t)(keys2[x0] & ((1ull << rank_bits) - 1))];
     const double km1b = __dmul_rn((double)(cstart[c + 1] - cstart[c] - 1), c_b[s]);
-    double pre = 0.0;
-    for (int32_t r = 0; r < n; r++) {
-        csr_c[csc_src[x0 + r]] = pre;
-        pre = __dadd_rn(pre, csc_delta[x0 + r]);
+    double carry = 0.0;
+    for (int32_t r0 = 0; r0 < n; r0 += 32) {                 // exclusive prefix, ascending
+        const int32_t r = r0 + lane;
+        const double d = (r < n) ? csc_delta[x0 + r] : 0.0;
+        double incl = d;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl = __dadd_rn(incl, v); }
+        double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 0.0;
+        if (r < n) csr_c[csc_src[x0 + r]] = __dadd_rn(carry, excl);
+        carry = __dadd_rn(carry, __shfl_sync(0xffffffffu, incl, 31));
     }
-    c_alpha[s] = pre;
-    double suf = 0.0;
-    for (int32_t r = n - 1; r >= 0; r--) {
-        const int32_t e = csc_src[x0 + r];
-        csr_c[e] = __dadd_rn(km1b, __dadd_rn(csr_c[e], suf));
-        suf = __dadd_rn(suf, csc_delta[x0 + r]);
+    if (lane == 0) c_alpha[s] = carry;
+    carry = 0.0;
+    for (int32_t r0 = 0; r0 < n; r0 += 32) {                 // exclusive suffix, descending
+        const int32_t r = n - 1 - (r0 + lane);
+        const double d = (r >= 0) ? csc_delta[x0 + r] : 0.0;
+        double incl = d;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl = __dadd_rn(incl, v); }
+        double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 0.0;
+        if (r >= 0) {
+            const int32_t e = csc_src[x0 + r];
+            csr_c[e] = __dadd_rn(km1b, __dadd_rn(csr_c[e], __dadd_rn(carry, excl)));
+        }
+        carry = __dadd_rn(carry, __shfl_sync(0xffffffffu, incl, 31));
     }
 }
 

@@ -215,17 +215,32 @@ def test_fine_seam_score_group_matches_coarse(golden, golden_ratings):
         assert np.array_equal(seen[u][0], coarse[u][0]) and np.array_equal(seen[u][1], coarse[u][1])
 
 
-def test_sharded_contexts_cover_all_users_once():
+@pytest.mark.parametrize("dyadic", [True, False])
+def test_sharded_contexts_cover_all_users_once(dyadic):
+    # dyadic scores -> sharded index (global statistics by exact atomics, local sort only);
+    # non-dyadic -> every rank keeps the replicated, order-preserving index
     r = datagen.generate("small")
-    full = by_user(gpu_run(r, 0.1, r.n_items, 20))
+    if not dyadic:
+        sc = (r.score * np.float32(0.74) + np.float32(0.013)).astype(np.float32)
+        r = datagen.Ratings("nd", r.n_users, r.n_items, r.user, r.item, sc, r.cl_user, r.cl_cluster, r.cluster_size, 0)
+    ref = gpu_run(r, 0.1, r.n_items, 20)
+    full = by_user(ref)
     merged = {}
     for rank in range(3):
-        part = by_user(gpu_run(r, 0.1, r.n_items, 20, shard_rank=rank, shard_count=3))
+        out = gpu_run(r, 0.1, r.n_items, 20, shard_rank=rank, shard_count=3)
+        assert out["stats"][2] == ref["stats"][2] and np.array_equal(out["stats"][0], ref["stats"][0]) \
+            and np.array_equal(out["stats"][1], ref["stats"][1])            # statistics are global on every rank
+        part = by_user(out)
         assert not (set(part) & set(merged))
         merged.update(part)
     assert set(merged) == set(full)
     for u in full:
         assert np.array_equal(merged[u][0], full[u][0]) and np.array_equal(merged[u][1], full[u][1])
+    # more shards than clusters, including empty shards
+    merged = {}
+    for rank in range(16):
+        merged.update(by_user(gpu_run(r, 0.1, r.n_items, 20, shard_rank=rank, shard_count=16)))
+    assert set(merged) == set(full) and all(np.array_equal(merged[u][0], full[u][0]) for u in full)
 
 
 def test_size_independent_properties_ml100k():
