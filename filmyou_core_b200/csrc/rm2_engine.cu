@@ -103,6 +103,7 @@ struct fy_rm2_ctx {
     DBuf<int32_t> cand[2], cand_cnt[2];
     DBuf<double> cand_score[2];
     DBuf<int> overflow;
+    DBuf<unsigned long long> cbound;
     DBuf<int32_t> chunk_ptr2[2];
     cudaStream_t stream_g = nullptr, stream_t = nullptr;   // H build / top-N run beside the score stream
     cudaEvent_t sync_ev[10] = {nullptr};
@@ -566,9 +567,17 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
         LAUNCH(ctx, k_csc_fill, cdiv(m, 256), 256, 0, keys2, ctx->csc_src.p, m, rank_bits, ctx->rank_cluster.p, ctx->cstart.p,
                ctx->csr_delta.p, ctx->csc_lu.p, ctx->csc_delta.p);
     }
+    ctx->cbound.need((size_t)KC * 3);
+    {
+        std::vector<unsigned long long> init((size_t)KC * 3);
+        for (int32_t c = 0; c < KC; c++) { init[3 * c] = 0; init[3 * c + 1] = 0; init[3 * c + 2] = ~0ull; }
+        CK(cudaMemcpyAsync(ctx->cbound.p, init.data(), init.size() * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));      // `init` dies at the end of this block
+    }
     if (n_slots > 0)
         LAUNCH(ctx, k_alpha_cuj, cdiv((int64_t)n_slots * 32, 256), 256, 0, ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, keys2, rank_bits,
-               ctx->rank_cluster.p, ctx->cstart.p, ctx->csc_src.p, ctx->csc_delta.p, n_slots, ctx->c_alpha.p, ctx->csr_c.p);
+               ctx->rank_cluster.p, ctx->cstart.p, ctx->csc_src.p, ctx->csc_delta.p, n_slots, ctx->c_alpha.p, ctx->csr_c.p,
+               ctx->cbound.p);
     CK(cudaEventRecord(ev_index, st));
 
     // ---------------- exponent-peel period L from a lower bound on t ----------------
@@ -606,6 +615,31 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     int cap = 64; while (cap < out_stride + 32) cap <<= 1;
     ctx->overflow.need(1);
     CK(cudaMemsetAsync(ctx->overflow.p, 0, sizeof(int), st));
+    // per-cluster plan of the 4-byte plane: float(H * 2^s) with fp32 math when the range of t allows a
+    // peel period >= 2, else the hi-word plane with fp64 math
+    struct Plan { int mode; int lf; int sexp; double scale; };
+    std::vector<Plan> plan((size_t)KC, Plan{1, 0, 0, 1.0});
+    if (use_hi && !ctx->use_ext) {
+        std::vector<unsigned long long> hb((size_t)KC * 3);
+        CK(cudaMemcpyAsync(hb.data(), ctx->cbound.p, hb.size() * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));      // sync B2: per-cluster bounds on alpha and b
+        for (int32_t c = 0; c < KC; c++) {
+            double a_max, b_max, b_min;
+            std::memcpy(&a_max, &hb[3 * c], 8); std::memcpy(&b_max, &hb[3 * c + 1], 8);
+            if (hb[3 * c + 2] == ~0ull) continue;
+            std::memcpy(&b_min, &hb[3 * c + 2], 8);
+            const double K = (double)(ctx->h_cstart[c + 1] - ctx->h_cstart[c]);
+            if (!(K >= 2.0) || !(b_min > 0.0) || !(a_max > 0.0)) continue;
+            // t <= alpha_max (1 + b_max) + b_max (K b_max + alpha_max)   (d <= 1);   t >= (K-1) b_min^2
+            const double t_max = a_max * (1.0 + b_max) + b_max * (K * b_max + a_max);
+            const double t_min = (K - 1.0) * b_min * b_min;
+            const double lo = std::log2(t_min) - 0.5, hi = std::log2(t_max) + 0.5;
+            const int sexp = -(int)std::lround(0.5 * (lo + hi));
+            const double half = std::max(hi + sexp, -(lo + sexp)) + 1.0;      // |log2(t 2^s)| <= half
+            const int lf = (int)std::floor(124.0 / half);
+            if (lf >= 2 && std::abs(sexp) < 1000) plan[c] = Plan{2, lf >= 4 ? 4 : 2, sexp, std::ldexp(1.0, sexp)};
+        }
+    }
     ctx->prof.bytes_per_term = use_hi ? 4.0 : 8.0;
     ctx->prof.exact_rerun = force_exact ? 1 : 0;
 
@@ -683,7 +717,7 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
             LAUNCH_ON(ctx, sG, k_build_H, dim3(I_c, nchunk), H_THREADS, smem, I_c, ld, n_bound - 1, slot0,
                       ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, ctx->c_alpha.p, ctx->csc_lu.p, ctx->csc_delta.p,
                       ctx->chunk_ptr2[hb].p, ctx->csr_loc.p, ctx->csr_delta.p, ctx->H[hb].p,
-                      use_hi ? ctx->Hh[hb].p : (uint32_t*)nullptr);
+                      use_hi ? ctx->Hh[hb].p : (uint32_t*)nullptr, plan[c].mode, plan[c].scale);
             seg_end(k, sG);
         }
         CK(cudaEventRecord(hReady[hb], sG));
@@ -703,7 +737,12 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
             LAUNCH_ON(ctx, sS, k_init_ustat, cdiv(nb, 256), 256, 0, ctx->ustat[sb].p, nb);
             {
                 const size_t k = seg_begin(SEG_SCORE, sS);
-                if (use_hi) {
+                if (use_hi && plan[c].mode == 2) {
+                    if (plan[c].lf >= 4)
+                        LAUNCH_ON(ctx, sS, k_score_f32<4>, grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, plan[c].scale, plan[c].sexp, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p);
+                    else
+                        LAUNCH_ON(ctx, sS, k_score_f32<2>, grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, plan[c].scale, plan[c].sexp, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p);
+                } else if (use_hi) {
                     switch (L) {
                         case 8: LAUNCH_ON(ctx, sS, k_score_hi<8>, grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
                         case 4: LAUNCH_ON(ctx, sS, k_score_hi<4>, grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;
@@ -733,7 +772,8 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
             if (use_hi) {
                 const size_t k = seg_begin(SEG_REFINE, sT);
                 LAUNCH_ON(ctx, sT, k_margin_gather, nb, 256, 0, ctx->scores[sb].p, I_c, ld, b0, ub, ctx->rowptr.p, out_stride,
-                          ctx->out_score.p, ctx->out_count.p, cap, ctx->cand[sb].p, ctx->cand_cnt[sb].p, ctx->overflow.p);
+                          ctx->out_score.p, ctx->out_count.p, cap, plan[c].mode == 2 ? 2.5e-7 : 4.8e-7, ctx->cand[sb].p,
+                          ctx->cand_cnt[sb].p, ctx->overflow.p);
                 LAUNCH_ON(ctx, sT, k_refine_score, dim3(nb, cdiv(cap, REFINE_THREADS / 32)), REFINE_THREADS, 0, ctx->H[hb].p, ld, b0,
                           slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, log_items, log_K, cap, ctx->cand[sb].p,
                           ctx->cand_cnt[sb].p, ctx->cand_score[sb].p);

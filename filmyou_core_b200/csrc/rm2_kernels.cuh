@@ -426,7 +426,8 @@ __global__ void k_alpha_cuj(const int32_t* __restrict__ c_start, const int32_t* 
                             const double* __restrict__ c_b, const uint64_t* __restrict__ keys2, int rank_bits,
                             const int32_t* __restrict__ rank_cluster, const int32_t* __restrict__ cstart,
                             const int32_t* __restrict__ csc_src, const double* __restrict__ csc_delta,
-                            int32_t n_slots, double* __restrict__ c_alpha, double* __restrict__ csr_c) {
+                            int32_t n_slots, double* __restrict__ c_alpha, double* __restrict__ csr_c,
+                            unsigned long long* __restrict__ cbound /* [3*KC]: max alpha, max b, min b (bits) */) {
     const int32_t s = (int32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (s >= n_slots) return;
@@ -445,7 +446,14 @@ __global__ void k_alpha_cuj(const int32_t* __restrict__ c_start, const int32_t* 
         if (r < n) csr_c[csc_src[x0 + r]] = __dadd_rn(carry, excl);
         carry = __dadd_rn(carry, __shfl_sync(0xffffffffu, incl, 31));
     }
-    if (lane == 0) c_alpha[s] = carry;
+    if (lane == 0) {
+        c_alpha[s] = carry;
+        // per-cluster bounds used to pick the scale / peel period of the float score kernel
+        const unsigned long long bb = (unsigned long long)__double_as_longlong(c_b[s]);
+        atomicMax(&cbound[3 * c], (unsigned long long)__double_as_longlong(carry));
+        atomicMax(&cbound[3 * c + 1], bb);
+        atomicMin(&cbound[3 * c + 2], bb);
+    }
     carry = 0.0;
     for (int32_t r0 = 0; r0 < n; r0 += 32) {                 // exclusive suffix, descending
         const int32_t r = n - 1 - (r0 + lane);
@@ -511,7 +519,8 @@ k_build_H(int32_t I_c, int32_t ld, int32_t n_slices, int32_t slot0,
           const double* __restrict__ c_b, const double* __restrict__ c_alpha,
           const int32_t* __restrict__ csc_lu, const double* __restrict__ csc_delta,
           const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ csr_loc,
-          const double* __restrict__ csr_delta, double* __restrict__ H, uint32_t* __restrict__ Hh) {
+          const double* __restrict__ csr_delta, double* __restrict__ H, uint32_t* __restrict__ Hh,
+          int plane_mode /* 1 = hi words, 2 = float(H * plane_scale) */, double plane_scale) {
     extern __shared__ double acc_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int32_t j = blockIdx.x;
@@ -586,17 +595,19 @@ k_build_H(int32_t I_c, int32_t ld, int32_t n_slices, int32_t slot0,
             o.x = __fma_rn(bj, al[t], acc[t]);
             o.y = __fma_rn(bj, al[t + 1], acc[t + 1]);
             *reinterpret_cast<double2*>(row + t) = o;
-            if (rowh) *reinterpret_cast<uint2*>(rowh + t) = make_uint2(hi_word_rn(o.x), hi_word_rn(o.y));
+            if (rowh) *reinterpret_cast<uint2*>(rowh + t) = (plane_mode == 2)
+                ? make_uint2(__float_as_uint((float)(o.x * plane_scale)), __float_as_uint((float)(o.y * plane_scale)))
+                : make_uint2(hi_word_rn(o.x), hi_word_rn(o.y));
         } else {
             const double o = __fma_rn(bj, al[t], acc[t]);
             row[t] = o;
-            if (rowh) rowh[t] = hi_word_rn(o);
+            if (rowh) rowh[t] = (plane_mode == 2) ? __float_as_uint((float)(o * plane_scale)) : hi_word_rn(o);
         }
     }
     if (sl == n_slices - 1)
         for (int32_t i = I_c + lane; i < ld; i += 32) {                              // padding columns
             H[(size_t)j * ld + i] = 1.0;
-            if (Hh) Hh[(size_t)j * ld + i] = 0x3ff00000u;
+            if (Hh) Hh[(size_t)j * ld + i] = (plane_mode == 2) ? 0x3f800000u : 0x3ff00000u;
         }
 }
 
@@ -829,11 +840,118 @@ k_score_hi(const uint32_t* __restrict__ Hh, int32_t I_c, int32_t ld, int32_t ran
     }
 }
 
+// Float variant of the approximate score kernel: the 4-byte plane holds float(H * 2^s) (s chosen per
+// cluster so that t * 2^s is centred on 1), t' = fmaf(b_i 2^s, c_uj, h') and the running product are
+// fp32 (full-rate pipe, no 64-bit register pairs to assemble), the exponent is peeled every LF factors.
+// Every factor carries <= 4 * 2^-24 relative error: |score~ - score| <= n_u * 2.4e-7.
+__device__ __forceinline__ void peel_exponent_f(float& p, int& ex) {
+    const int b = __float_as_int(p);
+    ex += (b >> 23) - 127;
+    p = __int_as_float((b & 0x007fffff) | 0x3f800000);
+}
+
+template <int LF>
+__global__ void __launch_bounds__(SCORE_THREADS)
+k_score_f32(const uint32_t* __restrict__ Hf, int32_t I_c, int32_t ld, int32_t rank_begin, int32_t slot0,
+            const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_loc,
+            const double* __restrict__ csr_c, const double* __restrict__ c_b, double plane_scale, int32_t scale_exp,
+            double log_items, double log_K, double* __restrict__ scores, unsigned long long* __restrict__ ustat) {
+    __shared__ int32_t s_j[SCORE_CHUNK];
+    __shared__ float s_c[SCORE_CHUNK];
+    __shared__ unsigned s_rated[SCOREH_TILE / 32];
+
+    const int32_t rank = rank_begin + blockIdx.x;
+    const int32_t tile0 = blockIdx.y * SCOREH_TILE;
+    const int32_t i = tile0 + 4 * threadIdx.x;
+    const int32_t e0 = rowptr[rank];
+    const int32_t n = rowptr[rank + 1] - e0;
+
+    if (threadIdx.x < SCOREH_TILE / 32) s_rated[threadIdx.x] = 0u;
+    float b[4], p[4];
+    int ex[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { b[q] = (i + q < I_c) ? (float)(c_b[slot0 + i + q] * plane_scale) : 0.0f; p[q] = 1.0f; ex[q] = 0; }
+    const uint32_t* __restrict__ Hc = Hf + i;
+
+    for (int32_t base = 0; base < n; base += SCORE_CHUNK) {
+        const int32_t cnt = min(SCORE_CHUNK, n - base);
+        __syncthreads();
+        for (int32_t k = threadIdx.x; k < cnt; k += SCORE_THREADS) {
+            const int32_t j = csr_loc[e0 + base + k];
+            s_j[k] = j;
+            s_c[k] = (float)csr_c[e0 + base + k];
+            const int32_t d = j - tile0;
+            if (d >= 0 && d < SCOREH_TILE) atomicOr(&s_rated[d >> 5], 1u << (d & 31));
+        }
+        __syncthreads();
+        int32_t k = 0;
+        for (; k + 8 <= cnt; k += 8) {
+            uint4 h[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) h[q] = __ldg(reinterpret_cast<const uint4*>(Hc + (size_t)s_j[k + q] * ld));
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const float c = s_c[k + q];
+                p[0] *= fmaf(b[0], c, __uint_as_float(h[q].x));
+                p[1] *= fmaf(b[1], c, __uint_as_float(h[q].y));
+                p[2] *= fmaf(b[2], c, __uint_as_float(h[q].z));
+                p[3] *= fmaf(b[3], c, __uint_as_float(h[q].w));
+                if ((q + 1) % LF == 0) {
+#pragma unroll
+                    for (int z = 0; z < 4; z++) peel_exponent_f(p[z], ex[z]);
+                }
+            }
+        }
+        for (; k < cnt; k++) {
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(Hc + (size_t)s_j[k] * ld));
+            const float c = s_c[k];
+            p[0] *= fmaf(b[0], c, __uint_as_float(h.x));
+            p[1] *= fmaf(b[1], c, __uint_as_float(h.y));
+            p[2] *= fmaf(b[2], c, __uint_as_float(h.z));
+            p[3] *= fmaf(b[3], c, __uint_as_float(h.w));
+            if (((k & 7) + 1) % LF == 0 || k + 1 == cnt) {
+#pragma unroll
+                for (int z = 0; z < 4; z++) peel_exponent_f(p[z], ex[z]);
+            }
+        }
+    }
+    __syncthreads();
+    const double pvpi = __dsub_rn(__dmul_rn((double)(n - 1), log_items), __dmul_rn((double)n, log_K));
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double NANV = __longlong_as_double(0x7ff8000000000000ll);
+    double s[4];
+    const int d = 4 * threadIdx.x;
+    const unsigned word = s_rated[d >> 5];
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const double et = (double)(ex[q] - n * scale_exp);               // undo the 2^s on each of the n factors
+        s[q] = fma(et, LN2_HI, fma(et, LN2_LO, log((double)p[q]))) + pvpi;
+        if (((word >> ((d + q) & 31)) & 1u) || i + q >= I_c) s[q] = NANV;
+        if (s[q] == s[q]) { const unsigned long long k = desc_key(s[q]); kmin = min(kmin, k); kmax = max(kmax, k); cnt++; }
+    }
+    double* dst = scores + (size_t)blockIdx.x * ld + i;
+    *reinterpret_cast<double2*>(dst) = make_double2(s[0], s[1]);
+    *reinterpret_cast<double2*>(dst + 2) = make_double2(s[2], s[3]);
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0) {
+        unsigned long long* st = ustat + 3 * (size_t)blockIdx.x;
+        atomicAdd(st, (unsigned long long)cnt);
+        atomicMin(st + 1, kmin);
+        atomicMax(st + 2, kmax);
+    }
+}
+
 // candidates that can be in the exact top-N: approximate score >= (N-th approximate score) - 2*eps
 __global__ void __launch_bounds__(256)
 k_margin_gather(const double* __restrict__ scores, int32_t I_c, int32_t ld, int32_t rank_begin, int32_t ub,
                 const int32_t* __restrict__ rowptr, int32_t out_stride, const double* __restrict__ out_score,
-                const int32_t* __restrict__ out_count, int32_t cap, int32_t* __restrict__ cand,
+                const int32_t* __restrict__ out_count, int32_t cap, double eps_per_term, int32_t* __restrict__ cand,
                 int32_t* __restrict__ cand_cnt, int* __restrict__ overflow) {
     __shared__ int s_n;
     const int32_t rank = rank_begin + blockIdx.x, orow = rank - ub;
@@ -842,7 +960,7 @@ k_margin_gather(const double* __restrict__ scores, int32_t I_c, int32_t ld, int3
     __syncthreads();
     if (n_out > 0) {
         const double n_u = (double)(rowptr[rank + 1] - rowptr[rank]);
-        const double eps = n_u * 4.8e-7 + 1e-9;                    // n_u * 2^-21 * 1.007 + fp64 slack
+        const double eps = n_u * eps_per_term + 1e-9;              // rigorous per-term bound + fp64 slack
         const double thr = out_score[(size_t)orow * out_stride + n_out - 1] - 2.0 * eps;
         const double* __restrict__ row = scores + (size_t)blockIdx.x * ld;
         for (int32_t i = threadIdx.x; i < I_c; i += blockDim.x) {
