@@ -119,7 +119,7 @@ def workload_figures(r):
 # ------------------------------------------------------------------------------------------------
 # CPU leg: the oracle ("port" of M/rm/AbstractRM2Reducer.java) on a bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(r, budget_s=15.0, seed=12345):
+def cpu_baseline(r, budget_s=8.0, seed=12345):
     from oracle import rm2_oracle as orc
     cores = os.cpu_count() or 1
     terms_total, i_c, n_u = workload_figures(r)
@@ -164,7 +164,7 @@ def run_reference_arm(args, r, workload):
     if rank != 0:
         return
     vals, last = [], None
-    budget = max(3.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    budget = max(2.0, min(8.0, 40.0 / max(1, args.steps + args.warmup)))
     for s in range(args.warmup + args.steps):
         last = cpu_baseline(r, budget_s=budget, seed=12345 + s)
         if s >= args.warmup:
@@ -288,7 +288,8 @@ def main():
                          sum(p["ms_gram"] for p in profs), sum(p["ms_index"] for p in profs),
                          sum(p["ms_topn"] for p in profs), float(launches),
                          float(sum(p["score_launches"] for p in profs)), sum(p["ms_refine"] for p in profs),
-                         float(profs[-1]["bytes_per_term"]), float(sum(p["exact_rerun"] for p in profs))],
+                         float(profs[-1]["bytes_per_term"]), float(sum(p["exact_rerun"] for p in profs)),
+                         float(profs[-1]["score_kernel"])],
                         dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -353,12 +354,13 @@ def main():
         s = s.tolist()
         per_rank.append({"ms_score": s[0], "score_bytes": s[1], "ms_gram": s[2], "ms_index": s[3], "ms_topn": s[4],
                          "launches": s[5], "score_launches": s[6], "ms_refine": s[7], "bytes_per_term": s[8],
-                         "exact_rerun": s[9]})
+                         "exact_rerun": s[9], "score_kernel": int(s[10])})
     worst = max(per_rank, key=lambda x: x["ms_score"])
     achieved = worst["score_bytes"] / (worst["ms_score"] * 1e-3) / 1e9 if worst["ms_score"] > 0 else 0.0
     hi = worst["bytes_per_term"] == 4.0
-    roofline = {"kernel": "fy::k_score_hi" if hi else "fy::k_score", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("k_score_hi" if hi else "k_score"),
+    kname = ("k_score", "k_score_hi", "k_score_f32")[worst["score_kernel"]]
+    roofline = {"kernel": "fy::" + kname, "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(kname),
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": worst["score_bytes"] / max(worst["score_launches"], 1),
                 "avg_launch_ms": worst["ms_score"] / max(worst["score_launches"], 1),

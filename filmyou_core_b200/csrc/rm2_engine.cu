@@ -641,6 +641,7 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
         }
     }
     ctx->prof.bytes_per_term = use_hi ? 4.0 : 8.0;
+    ctx->prof.score_kernel = 0;
     ctx->prof.exact_rerun = force_exact ? 1 : 0;
 
     // Three streams: H build of cluster c+1 (latency / DRAM-write bound) and top-N of cluster c-1 run
@@ -737,6 +738,7 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
             LAUNCH_ON(ctx, sS, k_init_ustat, cdiv(nb, 256), 256, 0, ctx->ustat[sb].p, nb);
             {
                 const size_t k = seg_begin(SEG_SCORE, sS);
+                if (use_hi) ctx->prof.score_kernel = std::max(ctx->prof.score_kernel, plan[c].mode);
                 if (use_hi && plan[c].mode == 2) {
                     if (plan[c].lf >= 4)
                         LAUNCH_ON(ctx, sS, k_score_f32<4>, grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, plan[c].scale, plan[c].sexp, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p);

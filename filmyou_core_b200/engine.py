@@ -12,7 +12,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-_SO = os.path.join(_HERE, "libfilmyou_rm2.so")
+_SO = os.environ.get("FY_RM2_LIB") or os.path.join(_HERE, "libfilmyou_rm2.so")   # FY_RM2_LIB: A/B-test another build
 _LIB = None
 
 STATUS = {
@@ -50,7 +50,7 @@ class Rm2Profile(C.Structure):
                 ("score_bytes", C.c_double), ("gram_bytes", C.c_double), ("users_scored", C.c_int64),
                 ("kernel_launches", C.c_int64), ("clusters_touched", C.c_int32), ("score_launches", C.c_int32),
                 ("ms_refine", C.c_double), ("bytes_per_term", C.c_double), ("exact_rerun", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("score_kernel", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

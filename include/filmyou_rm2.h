@@ -148,7 +148,7 @@ typedef struct fy_rm2_profile {
     double ms_refine;       /* margin gather + exact fp64 re-score of the candidates (auto mode) */
     double bytes_per_term;  /* 4 (hi-word plane) or 8 (fp64 plane): what score_bytes counts      */
     int32_t exact_rerun;    /* 1 if a candidate list overflowed and the run was redone in exact mode */
-    int32_t reserved;
+    int32_t score_kernel;   /* dominant kernel of the last run: 0 = k_score (fp64), 1 = k_score_hi, 2 = k_score_f32 */
 } fy_rm2_profile;
 int fy_rm2_get_profile(const fy_rm2_ctx* ctx, fy_rm2_profile* out);
 
