@@ -28,6 +28,12 @@ EXPORTS = [
     "fy_rm2_stats", "fy_rm2_result_count", "fy_rm2_users_scored", "fy_rm2_results", "fy_rm2_results_device", "fy_rm2_score_group",
     "fy_rm2_get_profile", "fy_cooc_counts", "fy_cooc_topk",
 ]
+# include/filmyou_seqfile.h
+SEQ_EXPORTS = [
+    "fy_seq_last_error", "fy_free", "fy_seq_write_intpair_float", "fy_seq_write_int_int", "fy_seq_write_int_double",
+    "fy_mapfile_write_int_double", "fy_seq_read_intpair_float", "fy_seq_read_int_int", "fy_seq_read_int_double",
+    "fy_rm2_run_files",
+]
 
 
 class Rm2Error(RuntimeError):
@@ -61,13 +67,13 @@ def library_path():
 
 
 def sources():
-    return sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cu"))
+    return sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cpp")))
 
 
 def build_library(force=False, verbose=False):
     """nvcc cross-compiles for sm_100a without a GPU (seconds)."""
     deps = sources() + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh")]
-    deps.append(os.path.join(_HERE, "..", "include", "filmyou_rm2.h"))
+    deps += [os.path.join(_HERE, "..", "include", h) for h in ("filmyou_rm2.h", "filmyou_seqfile.h")]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(d) <= os.path.getmtime(_SO) for d in deps):
         return _SO
     cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -114,7 +120,18 @@ def load_library():
     L.fy_rm2_get_profile.argtypes = [vp, C.POINTER(Rm2Profile)]
     L.fy_cooc_counts.argtypes = [vp, C.c_int32, C.c_int32, i32p, f64p]
     L.fy_cooc_topk.argtypes = [vp, C.c_int32, i32p, i32p, i32p]
-    for name in EXPORTS:
+    L.fy_seq_last_error.restype = C.c_char_p
+    L.fy_free.argtypes = [vp]
+    L.fy_free.restype = None
+    L.fy_seq_write_intpair_float.argtypes = [C.c_char_p, i32p, i32p, f32p, C.c_int64]
+    L.fy_seq_write_int_int.argtypes = [C.c_char_p, i32p, i32p, C.c_int64]
+    L.fy_seq_write_int_double.argtypes = [C.c_char_p, i32p, f64p, C.c_int64]
+    L.fy_mapfile_write_int_double.argtypes = [C.c_char_p, i32p, f64p, C.c_int64]
+    L.fy_seq_read_intpair_float.argtypes = [C.c_char_p, C.POINTER(i32p), C.POINTER(i32p), C.POINTER(f32p), C.POINTER(C.c_int64)]
+    L.fy_seq_read_int_int.argtypes = [C.c_char_p, C.POINTER(i32p), C.POINTER(i32p), C.POINTER(C.c_int64)]
+    L.fy_seq_read_int_double.argtypes = [C.c_char_p, C.POINTER(i32p), C.POINTER(f64p), C.POINTER(C.c_int64)]
+    L.fy_rm2_run_files.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, C.c_char_p]
+    for name in EXPORTS + SEQ_EXPORTS:
         getattr(L, name)
     _LIB = L
     return L
@@ -239,6 +256,13 @@ class Rm2Engine:
             self._h, int(cluster_id), int(split), int(n_splits), _ptr(group_user, C.c_int32),
             _ptr(group_user_sum, C.c_double), len(group_user), _ptr(r_user, C.c_int32), _ptr(r_item, C.c_int32),
             _ptr(r_score, C.c_float), len(r_user), _ptr(item_prob, C.c_double), len(item_prob) - 1))
+
+    def run_files(self, input_dir, clustering_dir, clustering_count_dir, number_of_clusters, output_dir, rm2_dir=None):
+        """RM2Job.run at the file level (SequenceFiles in, SequenceFile / MapFile out)."""
+        rc = self._L.fy_rm2_run_files(self._h, input_dir.encode(), clustering_dir.encode(), clustering_count_dir.encode(),
+                                      int(number_of_clusters), output_dir.encode(), rm2_dir.encode() if rm2_dir else None)
+        if rc != 0:
+            raise Rm2Error(rc, self._L.fy_seq_last_error().decode())
 
     def profile(self):
         p = Rm2Profile()

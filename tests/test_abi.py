@@ -11,20 +11,21 @@ from filmyou_core_b200 import engine
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
-    src = open(os.path.join(ROOT, "include", "filmyou_rm2.h")).read()
+def _declared(header="filmyou_rm2.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(fy_(?:rm2|cooc)_[a-z_0-9]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(fy_[a-z_0-9]+)\s*\(", src)))
 
 
 def test_header_and_binding_list_the_same_symbols():
     assert _declared() == sorted(engine.EXPORTS)
+    assert _declared("filmyou_seqfile.h") == sorted(engine.SEQ_EXPORTS)
 
 
 def test_library_builds_and_exports_every_declared_symbol():
     fy.build_library()
     L = fy.load_library()
-    for name in _declared():
+    for name in _declared() + _declared("filmyou_seqfile.h"):
         assert hasattr(L, name), name
     assert L.fy_rm2_abi_version() == 2
 

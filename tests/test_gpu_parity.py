@@ -310,3 +310,29 @@ def test_cpp_host_mirror(tmp_path):
     recs = [l.split() for l in out if l.startswith("rec")]
     assert [(int(a[1]), int(a[2])) for a in recs] == list(zip(want["user"].tolist(), want["item"].tolist()))
     assert np.allclose([float(a[3]) for a in recs], want["score32"], rtol=0, atol=1e-5)
+
+
+def test_file_level_job_reads_and_writes_sequence_files(golden, golden_ratings, tmp_path):
+    # T/rm/TestHDFSRM2.java:39-75 at the file level: fixtures written the way DataInitialization writes them
+    # (A/data, clustering/data with keys from 1, clusteringCount/data with keys from 0), job run through
+    # fy_rm2_run_files, outputs read back from rm2/output, rm2/userSum and the MapFile rm2/itemColl
+    from filmyou_core_b200 import seqfile
+    r = golden_ratings
+    base = tmp_path / "integrationTest"
+    for d in ("A", "clustering", "clusteringCount"):
+        (base / d).mkdir(parents=True)
+    seqfile.write_intpair_float(str(base / "A" / "data"), r.user, r.item, r.score)
+    seqfile.write_int_int(str(base / "clustering" / "data"), np.arange(1, 31), golden["clustering"])
+    seqfile.write_int_int(str(base / "clusteringCount" / "data"), np.arange(5), golden["clusteringCount"])
+    with fy.Rm2Engine(lam=0.5, number_of_items=100, top_n=1000) as eng:
+        eng.run_files(str(base / "A"), str(base / "clustering"), str(base / "clusteringCount"), golden["numberOfClusters"],
+                      str(base / "rm2" / "output"), str(base / "rm2"))
+    u, i, s = seqfile.read_intpair_float(str(base / "rm2" / "output"))
+    gold = {(int(a), int(b)): c for a, b, c in golden["recommendations"]}
+    assert len(u) == 507
+    for a, b, c in zip(u, i, s):
+        assert abs(gold[(int(a), int(b))] - float(c)) <= golden["accuracy"]          # compareIntPairFloatData
+    ku, vu = seqfile.read_int_double(str(base / "rm2" / "userSum"))
+    assert ku.tolist() == list(range(1, 31)) and np.array_equal(vu, np.array(golden["userSum"]))   # compareIntDoubleData
+    ki, vi = seqfile.read_int_double(str(base / "rm2" / "itemColl"))
+    assert ki.tolist() == list(range(1, 101)) and np.max(np.abs(vi - np.array(golden["itemColl"]))) <= 1e-18
