@@ -111,6 +111,34 @@ def test_candidate_overflow_falls_back_to_the_exact_stream():
     assert_parity(a, cpu_run(r, 0.1, 605, 5), REL, "overflow")
 
 
+def test_ml20m_sampled_users_vs_oracle():
+    # BASELINE.json headline shape (138 493 x 26 744, 20 M half-star ratings, 50 clusters): the whole job on
+    # the GPU, the literal CPU loop (2*K*n_u*c_u flops per user) on a seeded sample of light and medium users
+    r = datagen.generate("ml-20m")
+    got = gpu_run(r, 0.1, r.n_items, 100)
+    assert got["users_scored"] == r.n_users and len(got["user"]) == r.n_users * 100
+    assert got["profile"]["exact_rerun"] == 0
+    n_u = np.bincount(r.user, minlength=r.n_users + 1)
+    rng = np.random.default_rng(20)
+    light = rng.choice(np.flatnonzero((n_u >= 20) & (n_u <= 30)), size=6, replace=False)
+    medium = rng.choice(np.flatnonzero((n_u >= 100) & (n_u <= 140)), size=2, replace=False)
+    sample = np.concatenate([light, medium]).astype(np.int32)
+    want = cpu_run(r, 0.1, r.n_items, 100, only_users=sample)
+    g = by_user(got)
+    sub = {k: np.concatenate([np.full(len(g[int(u)][0]), int(u)) if k == "user" else
+                              (g[int(u)][0] if k == "item" else g[int(u)][1])
+                              for u in by_user(want)]) for k in ("user", "item", "score64")}
+    worst = assert_parity(sub, want, REL, "ml-20m sample")
+    assert worst < 1e-9
+    # size-independent properties over ALL users
+    items = got["item"].reshape(r.n_users, 100); scores = got["score64"].reshape(r.n_users, 100)
+    assert np.all(np.diff(scores, axis=1) <= 0)
+    assert np.all(np.sort(items, axis=1)[:, 1:] != np.sort(items, axis=1)[:, :-1])      # distinct per user
+    us, ip, tot = got["stats"]
+    ous, _, oip, otot = orc.stats(r.user, r.item, r.score, r.cl_user)
+    assert tot == otot and np.array_equal(us, ous) and np.array_equal(ip, oip[:len(ip)])
+
+
 def test_lambda_edge_cases():
     r = datagen.generate("tiny")
     for lam in (0.0, 1.0):
