@@ -13,6 +13,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_segmented_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -103,6 +104,9 @@ struct fy_rm2_ctx {
     DBuf<int32_t> cand[2], cand_cnt[2];
     DBuf<double> cand_score[2];
     DBuf<int> overflow;
+    DBuf<uint64_t> sort_keys[2];
+    DBuf<int32_t> sort_idx[2], seg_off;
+    DBuf<unsigned char> sort_tmp;
     DBuf<unsigned long long> cbound;
     DBuf<int32_t> chunk_ptr2[2];
     cudaStream_t stream_g = nullptr, stream_t = nullptr;   // H build / top-N run beside the score stream
@@ -600,8 +604,8 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     int32_t max_ic = 0;
     for (int32_t c = 0; c < KC; c++) max_ic = std::max(max_ic, h_icount_global[c]);   // same stride on every rank
     const int32_t out_stride = std::max(1, std::min(ctx->prm.top_n, max_ic));
-    if (out_stride > TOPN_MAX_SELECT)
-        return ctx->fail(FY_E_UNSUPPORTED, "min(numberOfRecommendations, items per cluster) = %d exceeds %d", out_stride, TOPN_MAX_SELECT);
+    // min(N, I_c) beyond the shared-memory select/sort bound: whole-row stable segmented sort (exact stream)
+    const bool big_n = out_stride > TOPN_MAX_SELECT;
     ctx->out_stride = out_stride;
     ctx->out_item.need((size_t)std::max(n_rows, 1) * out_stride);
     ctx->out_score.need((size_t)std::max(n_rows, 1) * out_stride);
@@ -666,7 +670,7 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     std::vector<Seg> segs;
     auto seg_begin = [&](int kind, cudaStream_t strm) { CK(cudaEventRecord(ctx->ev(evi), strm)); segs.push_back(Seg{kind, evi, 0}); evi++; return segs.size() - 1; };
     auto seg_end = [&](size_t k, cudaStream_t strm) { CK(cudaEventRecord(ctx->ev(evi), strm)); segs[k].e1 = evi; evi++; };
-    const size_t SCORE_BUF_BYTES = (size_t)2 << 30;
+    const size_t SCORE_BUF_BYTES = big_n ? ((size_t)1 << 29) : ((size_t)2 << 30);
     auto h_geometry = [&](int32_t I_c, int32_t& ld, int32_t& slice_w, int32_t& chunk_w, int32_t& nchunk, int32_t& n_bound) {
         ld = cdiv(I_c, SCOREH_TILE) * SCOREH_TILE;
         slice_w = H_SLICE;
@@ -694,6 +698,11 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
             if (b == 1 && n_touched < 2) need_h = need_cp = 0;     // a single cluster needs one H
             if (b == 1 && n_batches < 2) need_sc = need_us = 0;
             ctx->H[b].need(need_h); ctx->chunk_ptr2[b].need(need_cp); ctx->scores[b].need(need_sc); ctx->ustat[b].need(need_us);
+            if (big_n && b == 0) {
+                ctx->sort_keys[0].need(need_sc); ctx->sort_keys[1].need(need_sc); ctx->sort_idx[0].need(need_sc); ctx->sort_idx[1].need(need_sc);
+                ctx->seg_off.need(need_us / 3 + 2);
+                if (need_sc >= ((size_t)1 << 31)) return ctx->fail(FY_E_UNSUPPORTED, "score batch too large for the segmented sort");
+            }
             if (use_hi) { ctx->Hh[b].need(need_h); ctx->cand[b].need(need_us / 3 * cap); ctx->cand_score[b].need(need_us / 3 * cap); ctx->cand_cnt[b].need(need_us / 3); }
         }
     }
@@ -727,9 +736,9 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
         CK(cudaStreamWaitEvent(sS, hReady[hb], 0));
         const double log_K = std::log((double)K_c);                        // :329
         const int32_t batch = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)(r1 - r0), SCORE_BUF_BYTES / ((size_t)ld * 8)));
-        int P2 = 1; while (P2 < std::min(ctx->prm.top_n, I_c)) P2 <<= 1;
+        int P2 = 1; while (P2 < std::min(std::min(ctx->prm.top_n, I_c), (int32_t)TOPN_MAX_SELECT)) P2 <<= 1;
         const size_t topn_smem = (size_t)P2 * 12;
-        if (topn_smem > 36 * 1024) CK(cudaFuncSetAttribute(k_topn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topn_smem));
+        if (!big_n && topn_smem > 36 * 1024) CK(cudaFuncSetAttribute(k_topn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topn_smem));
         if (use_hi && (size_t)cap * 12 > 40 * 1024) CK(cudaFuncSetAttribute(k_refine_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 12));
         for (int32_t b0 = r0; b0 < r1; b0 += batch) {
             const int32_t nb = std::min(batch, r1 - b0);
@@ -764,7 +773,22 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
             CK(cudaEventRecord(sReady[sb], sS));
             s_used[sb] = true;
             CK(cudaStreamWaitEvent(sT, sReady[sb], 0));
-            {
+            if (big_n) {
+                const size_t k = seg_begin(SEG_TOPN, sT);
+                const int64_t tot = (int64_t)nb * ld;
+                LAUNCH_ON(ctx, sT, k_sort_prepare, cdiv(tot, 256), 256, 0, ctx->scores[sb].p, I_c, ld, tot, ctx->sort_keys[0].p, ctx->sort_idx[0].p);
+                LAUNCH_ON(ctx, sT, k_seg_offsets, cdiv(nb + 1, 256), 256, 0, ctx->seg_off.p, nb, ld);
+                size_t tmp = 0;
+                CK(cub::DeviceSegmentedSort::StableSortPairs(nullptr, tmp, ctx->sort_keys[0].p, ctx->sort_keys[1].p, ctx->sort_idx[0].p,
+                                                             ctx->sort_idx[1].p, tot, nb, ctx->seg_off.p, ctx->seg_off.p + 1, sT));
+                if (tmp > ctx->sort_tmp.cap) { CK(cudaStreamSynchronize(sT)); ctx->sort_tmp.need(tmp); }
+                CK(cub::DeviceSegmentedSort::StableSortPairs(ctx->sort_tmp.p, tmp, ctx->sort_keys[0].p, ctx->sort_keys[1].p, ctx->sort_idx[0].p,
+                                                             ctx->sort_idx[1].p, tot, nb, ctx->seg_off.p, ctx->seg_off.p + 1, sT));
+                LAUNCH_ON(ctx, sT, k_emit_sorted, nb, 256, 0, ctx->sort_keys[1].p, ctx->sort_idx[1].p, ctx->ustat[sb].p, ld, b0, ub, slot0,
+                          ctx->prm.top_n, out_stride, ctx->prm.filter_users, ctx->split, ctx->n_splits, ctx->rank_userid.p,
+                          ctx->c_item.p, ctx->out_item.p, ctx->out_score.p, ctx->out_count.p);
+                seg_end(k, sT);
+            } else {
                 const size_t k = seg_begin(SEG_TOPN, sT);
                 LAUNCH_ON(ctx, sT, k_topn, nb, TOPN_THREADS, topn_smem, ctx->scores[sb].p, ctx->ustat[sb].p, I_c, ld, b0, slot0,
                           ctx->prm.top_n, out_stride, ctx->prm.filter_users, ctx->split, ctx->n_splits, ctx->rank_userid.p,

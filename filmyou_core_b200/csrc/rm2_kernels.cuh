@@ -1214,6 +1214,40 @@ k_topn(const double* __restrict__ scores, const unsigned long long* __restrict__
     if (tid == 0) out_count[orow] = n_out;
 }
 
+// ---- large-N path (min(N, I_c) > TOPN_MAX_SELECT): whole-row stable segmented sort ----
+__global__ void k_sort_prepare(const double* __restrict__ scores, int32_t I_c, int32_t ld, int64_t n,
+                               uint64_t* __restrict__ keys, int32_t* __restrict__ idx) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int32_t i = (int32_t)(t % ld);
+    const double s = scores[t];
+    keys[t] = (i < I_c && s == s) ? desc_key(s) : ~0ull;      // non-candidates sort last
+    idx[t] = i;
+}
+
+// first min(N, c_u) entries of every user's sorted row (stable sort: equal scores keep ascending item id)
+__global__ void k_emit_sorted(const uint64_t* __restrict__ keys, const int32_t* __restrict__ idx,
+                              const unsigned long long* __restrict__ ustat, int32_t ld, int32_t rank_begin, int32_t ub,
+                              int32_t slot0, int32_t top_n, int32_t out_stride, int32_t filter_users, int32_t split,
+                              int32_t n_splits, const int32_t* __restrict__ rank_userid, const int32_t* __restrict__ c_item,
+                              int32_t* __restrict__ out_item, double* __restrict__ out_score, int32_t* __restrict__ out_count) {
+    const int32_t rank = rank_begin + blockIdx.x, orow = rank - ub;
+    const int32_t uid = rank_userid[rank];
+    const int c_u = (int)ustat[3 * (size_t)blockIdx.x];
+    int n_out = min(top_n, c_u);
+    if (uid < filter_users || (n_splits > 1 && (uid % n_splits) != split)) n_out = 0;
+    for (int32_t t = threadIdx.x; t < n_out; t += blockDim.x) {
+        out_item[(size_t)orow * out_stride + t] = c_item[slot0 + idx[(size_t)blockIdx.x * ld + t]];
+        out_score[(size_t)orow * out_stride + t] = key_to_score(keys[(size_t)blockIdx.x * ld + t]);
+    }
+    if (threadIdx.x == 0) out_count[orow] = n_out;
+}
+
+__global__ void k_seg_offsets(int32_t* __restrict__ off, int32_t n, int32_t ld) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) off[i] = i * ld;
+}
+
 __global__ void k_init_ustat(unsigned long long* __restrict__ ustat, int32_t n) {
     const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { ustat[3 * (size_t)i] = 0ull; ustat[3 * (size_t)i + 1] = ~0ull; ustat[3 * (size_t)i + 2] = 0ull; }

@@ -139,6 +139,16 @@ def test_ml20m_sampled_users_vs_oracle():
     assert tot == otot and np.array_equal(us, ous) and np.array_equal(ip, oip[:len(ip)])
 
 
+def test_more_than_4096_recommendations_per_user():
+    # min(numberOfRecommendations, items of the cluster) beyond the shared-memory select bound: the engine
+    # switches to a whole-row stable segmented sort; everything a user has not rated is emitted, in order
+    r = datagen.generate("big-n", n_users=100, n_items=5200, nnz=26000, n_clusters=1, seed=5)
+    got = gpu_run(r, 0.1, r.n_items, 6000)
+    want = cpu_run(r, 0.1, r.n_items, 6000)
+    assert max(len(v[0]) for v in by_user(want).values()) > 4096
+    assert_parity(got, want, REL, "N > 4096")
+
+
 def test_lambda_edge_cases():
     r = datagen.generate("tiny")
     for lam in (0.0, 1.0):
