@@ -723,7 +723,8 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
             const size_t k = seg_begin(SEG_GRAM, sG);
             LAUNCH_ON(ctx, sG, k_chunk_ptr, cdiv((int64_t)K_c * n_bound, 256), 256, 0, cs, K_c, n_bound, slice_w,
                       ctx->rowptr.p, ctx->csr_loc.p, ctx->chunk_ptr2[hb].p);
-            const size_t smem = (size_t)chunk_w * sizeof(double);      // 32 KB: 8 warps x 512 doubles
+            const size_t smem = (size_t)chunk_w * sizeof(double);      // 8 warps x H_SLICE doubles
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_build_H, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             LAUNCH_ON(ctx, sG, k_build_H, dim3(I_c, nchunk), H_THREADS, smem, I_c, ld, n_bound - 1, slot0,
                       ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, ctx->c_alpha.p, ctx->csc_lu.p, ctx->csc_delta.p,
                       ctx->chunk_ptr2[hb].p, ctx->csr_loc.p, ctx->csr_delta.p, ctx->H[hb].p,
