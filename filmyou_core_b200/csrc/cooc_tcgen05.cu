@@ -79,7 +79,8 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_cooc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            int32_t* __restrict__ C, int n_items, int ldc, int num_k_blocks, int n_tiles_m, int n_tiles_n) {
+            int32_t* __restrict__ C, int m_rows, int n_items, int ldc, int num_k_blocks, int n_tiles_m, int n_tiles_n,
+            int symmetric) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment
@@ -101,7 +102,7 @@ k_cooc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int m_tile = sid * GROUP_M + rem % gm, n_tile = rem / gm;
     // C is symmetric: tiles entirely below the diagonal are produced by the mirrored store of their
     // transposes, so they are skipped (uniform exit before any barrier / TMEM allocation).
-    if ((n_tile + 1) * BN <= m_tile * BM) return;
+    if (symmetric && (n_tile + 1) * BN <= m_tile * BM) return;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
@@ -172,7 +173,7 @@ k_cooc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (m < n_items) {
+            if (m < m_rows) {
 #pragma unroll
                 for (int x = 0; x < 8; x++) {
                     int4 o = make_int4((int)v[4 * x], (int)v[4 * x + 1], (int)v[4 * x + 2], (int)v[4 * x + 3]);
@@ -181,10 +182,12 @@ k_cooc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             // mirrored store C[n][m] = C[m][n]: lanes hold consecutive m, so each store is one
             // contiguous 128-byte segment of row n
-            const int nb = n_tile * BN + c * 32;
+            if (symmetric) {
+                const int nb = n_tile * BN + c * 32;
 #pragma unroll
-            for (int x = 0; x < 32; x++)
-                if (nb + x < n_items) C[(size_t)(nb + x) * ldc + m] = (int32_t)v[x];
+                for (int x = 0; x < 32; x++)
+                    if (nb + x < n_items) C[(size_t)(nb + x) * ldc + m] = (int32_t)v[x];
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -201,10 +204,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 }  // namespace cooc
 
-// Internal launcher used by fy_cooc_counts (rm2_engine.cu).  Bt: [n_items x k_pad] uint8, k_pad a
-// multiple of 128; C: [n_items x ldc] int32 with ldc a multiple of 256 and >= n_items.
-extern "C" int fyi_cooc_gemm_launch(const uint8_t* Bt, int n_items, int k_pad, int32_t* C, int ldc, void* stream,
-                                    char* err, size_t errlen) {
+// Internal launchers (rm2_engine.cu).  C[a_rows x ldc] = A[a_rows x k_pad] * B[b_rows x k_pad]^T on uint8
+// operands, int32 result; k_pad a multiple of 128, ldc a multiple of 256 and >= b_rows.  symmetric = 1
+// (A == B): only tiles touching the upper triangle are computed and every tile is also stored mirrored.
+extern "C" int fyi_gemm_u8_nt(const uint8_t* A, int a_rows, const uint8_t* B, int b_rows, int k_pad, int32_t* C, int ldc,
+                              int symmetric, void* stream, char* err, size_t errlen) {
     using namespace cooc;
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
@@ -217,22 +221,31 @@ extern "C" int fyi_cooc_gemm_launch(const uint8_t* Bt, int n_items, int k_pad, i
         }
         encode = (EncodeTiledFn)fn;
     }
-    if (k_pad % BK != 0 || ldc % BN != 0 || ldc < n_items) { snprintf(err, errlen, "bad co-occurrence geometry"); return -1; }
+    if (k_pad % BK != 0 || ldc % BN != 0 || ldc < b_rows || a_rows <= 0 || b_rows <= 0 || (symmetric && (A != B || a_rows != b_rows))) {
+        snprintf(err, errlen, "bad GEMM geometry");
+        return -1;
+    }
     CUtensorMap tmA, tmB;
-    const cuuint64_t gdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)n_items};
+    const cuuint64_t gdimA[2] = {(cuuint64_t)k_pad, (cuuint64_t)a_rows}, gdimB[2] = {(cuuint64_t)k_pad, (cuuint64_t)b_rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)k_pad};
     const cuuint32_t estr[2] = {1, 1};
     const cuuint32_t boxA[2] = {(cuuint32_t)BK, (cuuint32_t)BM}, boxB[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
-    CUresult r1 = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)Bt, gdim, gstride, boxA, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r1 = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)A, gdimA, gstride, boxA, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    CUresult r2 = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)Bt, gdim, gstride, boxB, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r2 = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)B, gdimB, gstride, boxB, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2); return -7; }
     cudaError_t e = cudaFuncSetAttribute(k_cooc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -7; }
-    const int nt_n = (n_items + BN - 1) / BN, nt_m = (n_items + BM - 1) / BM;
-    k_cooc_gemm<<<nt_n * nt_m, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, C, n_items, ldc, k_pad / BK, nt_m, nt_n);
+    const int nt_n = (b_rows + BN - 1) / BN, nt_m = (a_rows + BM - 1) / BM;
+    k_cooc_gemm<<<nt_n * nt_m, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, C, a_rows, b_rows, ldc, k_pad / BK, nt_m, nt_n,
+                                                                              symmetric);
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(err, errlen, "k_cooc_gemm launch: %s", cudaGetErrorString(e)); return -7; }
     return 0;
+}
+
+extern "C" int fyi_cooc_gemm_launch(const uint8_t* Bt, int n_items, int k_pad, int32_t* C, int ldc, void* stream,
+                                    char* err, size_t errlen) {
+    return fyi_gemm_u8_nt(Bt, n_items, Bt, n_items, k_pad, C, ldc, 1, stream, err, errlen);
 }

@@ -1031,6 +1031,93 @@ extern "C" int fy_cooc_counts(fy_rm2_ctx* ctx, int32_t n_user_ids, int32_t n_ite
     });
 }
 
+extern "C" int fyi_gemm_u8_nt(const uint8_t* A, int a_rows, const uint8_t* B, int b_rows, int k_pad, int32_t* C, int ldc,
+                              int symmetric, void* stream, char* err, size_t errlen);
+
+// ---------------------------------------------------------------------------------------------
+// a9 / f3: kNN neighbourhood provider.  user-user co-occurrence counts (B B^T on the binarised matrix,
+// the same int8 tcgen05 GEMM, in blocks of rows because U^2 counts do not fit) and per-user top-k
+// neighbours (k_topn; self excluded, ties by ascending user id).  The reference has NO such step
+// (its neighbourhood is the user's cluster): checked against an integer CPU restatement
+// only; not wired into the RM2 scoring.
+// ---------------------------------------------------------------------------------------------
+extern "C" int fy_knn_neighbours(fy_rm2_ctx* ctx, int32_t n_user_ids, int32_t n_items, int32_t k,
+                                 int32_t* neighbour_out, int32_t* count_out, int32_t* n_out, double* ms_gemm_out) {
+    if (!ctx) return FY_E_ARG;
+    if (!ctx->have_ratings) return ctx->fail(FY_E_STATE, "fy_knn_neighbours needs fy_rm2_set_ratings first");
+    if (!neighbour_out || n_user_ids <= 0 || n_items <= ctx->max_item) return ctx->fail(FY_E_ARG, "bad argument (n_items must exceed the largest rated item id %d)", ctx->max_item);
+    if (k <= 0 || k > fy::TOPN_MAX_SELECT) return ctx->fail(FY_E_UNSUPPORTED, "k outside [1, %d]", fy::TOPN_MAX_SELECT);
+    return guarded(ctx, [&]() {
+        using namespace fy;
+        CK(cudaSetDevice(ctx->prm.device));
+        cudaStream_t st = ctx->stream;
+        const int32_t U = n_user_ids;
+        const int32_t k_pad = cdiv(n_items, 128) * 128, ldc = cdiv(U, 256) * 256, ld = cdiv(U, SCORE_TILE) * SCORE_TILE;
+        const int32_t R = (int32_t)std::min<int64_t>(cdiv(U, 128) * 128, 4096);          // rows of C per GEMM
+        const int32_t batch = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)R, ((size_t)1 << 30) / ((size_t)ld * 8)));
+        ctx->cooc_bt.need((size_t)U * k_pad);
+        ctx->cooc_counts.need((size_t)R * ldc);
+        ctx->scores[0].need((size_t)batch * ld); ctx->ustat[0].need((size_t)batch * 3);
+        ctx->cooc_iota.need(U); ctx->cooc_zero.need(U);
+        ctx->cooc_out_item.need((size_t)U * k); ctx->cooc_out_score.need((size_t)U * k); ctx->cooc_out_cnt.need(U);
+        ctx->flags.need(DF_COUNT);
+        CK(cudaMemsetAsync(ctx->flags.p, 0, sizeof(int) * DF_COUNT, st));
+        CK(cudaMemsetAsync(ctx->cooc_bt.p, 0, (size_t)U * k_pad, st));
+        // Bu[user][item]: k_binarise with the roles of the two ids swapped
+        LAUNCH(ctx, k_binarise, cdiv(ctx->nnz, 256), 256, 0, ctx->in_item.p, ctx->in_user.p, ctx->in_score.p, ctx->nnz,
+               n_items, U, k_pad, ctx->cooc_bt.p, ctx->flags.p);
+        LAUNCH(ctx, k_iota, cdiv(U, 256), 256, 0, ctx->cooc_iota.p, U);
+        CK(cudaMemsetAsync(ctx->cooc_zero.p, 0, (size_t)U * 4, st));
+        CK(cudaMemsetAsync(ctx->cooc_out_cnt.p, 0, (size_t)U * 4, st));
+        int P2 = 1; while (P2 < std::min(k, U)) P2 <<= 1;
+        const size_t topn_smem = (size_t)P2 * 12;
+        if (topn_smem > 36 * 1024) CK(cudaFuncSetAttribute(k_topn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topn_smem));
+        double ms_gemm = 0.0;
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+        size_t evi = 0;
+        for (int32_t r0 = 0; r0 < U; r0 += R) {
+            const int32_t rows = std::min(R, U - r0);
+            cudaEvent_t e0 = ctx->ev(evi++), e1 = ctx->ev(evi++);
+            CK(cudaEventRecord(e0, st));
+            const int rc = fyi_gemm_u8_nt(ctx->cooc_bt.p + (size_t)r0 * k_pad, rows, ctx->cooc_bt.p, U, k_pad, ctx->cooc_counts.p, ldc, 0,
+                                          (void*)st, ctx->err, sizeof(ctx->err));
+            if (rc != 0) return rc;
+            ctx->launches++;
+            CK(cudaEventRecord(e1, st));
+            evs.emplace_back(e0, e1);
+            for (int32_t b0 = 0; b0 < rows; b0 += batch) {
+                const int32_t nb = std::min(batch, rows - b0);
+                LAUNCH(ctx, k_init_ustat, cdiv(nb, 256), 256, 0, ctx->ustat[0].p, nb);
+                LAUNCH(ctx, k_cooc_scores, dim3(nb, ld / SCORE_TILE), SCORE_THREADS, 0, ctx->cooc_counts.p, U, ldc, ld, b0, r0,
+                       ctx->scores[0].p, ctx->ustat[0].p);
+                LAUNCH(ctx, k_topn, nb, TOPN_THREADS, topn_smem, ctx->scores[0].p, ctx->ustat[0].p, U, ld, 0, 0, k, k, 0, 0, 1,
+                       ctx->cooc_zero.p, ctx->cooc_iota.p, r0 + b0, ctx->cooc_out_item.p, ctx->cooc_out_score.p, ctx->cooc_out_cnt.p);
+            }
+        }
+        int h_flags[DF_COUNT];
+        std::vector<double> sc((size_t)U * k);
+        std::vector<int32_t> cnt((size_t)U);
+        CK(cudaMemcpyAsync(h_flags, ctx->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(neighbour_out, ctx->cooc_out_item.p, (size_t)U * k * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(sc.data(), ctx->cooc_out_score.p, (size_t)U * k * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(cnt.data(), ctx->cooc_out_cnt.p, (size_t)U * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_flags[DF_BAD_ITEM]) return ctx->fail(FY_E_ARG, "user or item id outside [0, n_user_ids) x [0, n_items)");
+        for (auto& e : evs) { float ms = 0; CK(cudaEventElapsedTime(&ms, e.first, e.second)); ms_gemm += ms; }
+        if (ms_gemm_out) *ms_gemm_out = ms_gemm;
+        for (int32_t r = 0; r < U; r++) {
+            if (n_out) n_out[r] = cnt[r];
+            for (int32_t t = 0; t < k; t++) {
+                const size_t o = (size_t)r * k + t;
+                if (t < cnt[r]) { if (count_out) count_out[o] = (int32_t)sc[o]; }
+                else { neighbour_out[o] = -1; if (count_out) count_out[o] = 0; }
+            }
+        }
+        ctx->cooc_items = 0;       // the count matrix no longer holds item-item counts
+        return (int)FY_OK;
+    });
+}
+
 extern "C" int fy_cooc_topk(fy_rm2_ctx* ctx, int32_t k, int32_t* item_out, int32_t* count_out, int32_t* n_out) {
     if (!ctx) return FY_E_ARG;
     if (ctx->cooc_items <= 0) return ctx->fail(FY_E_STATE, "fy_cooc_topk needs fy_cooc_counts first");
@@ -1053,7 +1140,7 @@ extern "C" int fy_cooc_topk(fy_rm2_ctx* ctx, int32_t k, int32_t* item_out, int32
         for (int32_t r0 = 0; r0 < n; r0 += batch) {
             const int32_t nb = std::min(batch, n - r0);
             LAUNCH(ctx, k_init_ustat, cdiv(nb, 256), 256, 0, ctx->ustat[0].p, nb);
-            LAUNCH(ctx, k_cooc_scores, dim3(nb, ld / SCORE_TILE), SCORE_THREADS, 0, ctx->cooc_counts.p, n, ldc, ld, r0,
+            LAUNCH(ctx, k_cooc_scores, dim3(nb, ld / SCORE_TILE), SCORE_THREADS, 0, ctx->cooc_counts.p, n, ldc, ld, r0, 0,
                    ctx->scores[0].p, ctx->ustat[0].p);
             LAUNCH(ctx, k_topn, nb, TOPN_THREADS, topn_smem, ctx->scores[0].p, ctx->ustat[0].p, n, ld, 0, 0, k, k, 0, 0, 1,
                    ctx->cooc_zero.p, ctx->cooc_iota.p, r0, ctx->cooc_out_item.p, ctx->cooc_out_score.p, ctx->cooc_out_cnt.p);

@@ -1270,14 +1270,15 @@ __global__ void k_binarise(const int32_t* __restrict__ r_user, const int32_t* __
 // rows [row0, row0+gridDim.x) of the count matrix -> score rows for k_topn: NaN for the item itself
 // (excludeSelfSimilarity) and for zero counts (RowSimilarityJob emits no zero similarities)
 __global__ void __launch_bounds__(SCORE_THREADS)
-k_cooc_scores(const int32_t* __restrict__ C, int32_t n_items, int32_t ldc, int32_t ld, int32_t row0,
+k_cooc_scores(const int32_t* __restrict__ C, int32_t n_items, int32_t ldc, int32_t ld, int32_t row0, int32_t self0,
               double* __restrict__ scores, unsigned long long* __restrict__ ustat) {
-    const int32_t row = row0 + blockIdx.x;
+    const int32_t row = row0 + blockIdx.x;               // row of C
+    const int32_t self = self0 + row;                    // the column excluded as "self"
     const int32_t i = blockIdx.y * SCORE_TILE + 2 * threadIdx.x;
     const double NANV = __longlong_as_double(0x7ff8000000000000ll);
     double s0 = NANV, s1 = NANV;
-    if (i < n_items && i != row) { const int32_t c = C[(size_t)row * ldc + i]; if (c > 0) s0 = (double)c; }
-    if (i + 1 < n_items && i + 1 != row) { const int32_t c = C[(size_t)row * ldc + i + 1]; if (c > 0) s1 = (double)c; }
+    if (i < n_items && i != self) { const int32_t c = C[(size_t)row * ldc + i]; if (c > 0) s0 = (double)c; }
+    if (i + 1 < n_items && i + 1 != self) { const int32_t c = C[(size_t)row * ldc + i + 1]; if (c > 0) s1 = (double)c; }
     double2 out; out.x = s0; out.y = s1;
     *reinterpret_cast<double2*>(scores + (size_t)blockIdx.x * ld + i) = out;
     const bool v0 = (s0 == s0), v1 = (s1 == s1);

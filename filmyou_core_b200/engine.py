@@ -26,7 +26,7 @@ EXPORTS = [
     "fy_rm2_abi_version", "fy_rm2_default_params", "fy_rm2_create", "fy_rm2_destroy", "fy_rm2_last_error",
     "fy_rm2_set_stream", "fy_rm2_set_ratings", "fy_rm2_set_clustering", "fy_rm2_run", "fy_rm2_max_item",
     "fy_rm2_stats", "fy_rm2_result_count", "fy_rm2_users_scored", "fy_rm2_results", "fy_rm2_results_device", "fy_rm2_score_group",
-    "fy_rm2_get_profile", "fy_cooc_counts", "fy_cooc_topk",
+    "fy_rm2_get_profile", "fy_cooc_counts", "fy_cooc_topk", "fy_knn_neighbours",
 ]
 # include/filmyou_seqfile.h
 SEQ_EXPORTS = [
@@ -120,6 +120,7 @@ def load_library():
     L.fy_rm2_get_profile.argtypes = [vp, C.POINTER(Rm2Profile)]
     L.fy_cooc_counts.argtypes = [vp, C.c_int32, C.c_int32, i32p, f64p]
     L.fy_cooc_topk.argtypes = [vp, C.c_int32, i32p, i32p, i32p]
+    L.fy_knn_neighbours.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, i32p, i32p, i32p, f64p]
     L.fy_seq_last_error.restype = C.c_char_p
     L.fy_free.argtypes = [vp]
     L.fy_free.restype = None
@@ -275,6 +276,16 @@ class Rm2Engine:
         self._check(self._L.fy_cooc_counts(self._h, int(n_user_ids), int(n_items),
                                             _ptr(out, C.c_int32) if want_counts else None, C.byref(ms)))
         return out, ms.value
+
+    def knn_neighbours(self, n_user_ids, n_items, k):
+        """(neighbours[n_user_ids, k] (-1 padded), counts, n, ms_gemm): top-k co-rating users per user id."""
+        nb = np.zeros((n_user_ids, k), np.int32)
+        cnt = np.zeros((n_user_ids, k), np.int32)
+        n = np.zeros(n_user_ids, np.int32)
+        ms = C.c_double(0)
+        self._check(self._L.fy_knn_neighbours(self._h, int(n_user_ids), int(n_items), int(k), _ptr(nb, C.c_int32),
+                                               _ptr(cnt, C.c_int32), _ptr(n, C.c_int32), C.byref(ms)))
+        return nb, cnt, n, ms.value
 
     def cooc_topk(self, n_items, k):
         items = np.zeros((n_items, k), np.int32)

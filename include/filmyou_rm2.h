@@ -164,6 +164,15 @@ int fy_cooc_counts(fy_rm2_ctx* ctx, int32_t n_user_ids, int32_t n_items, int32_t
 int fy_cooc_topk(fy_rm2_ctx* ctx, int32_t k, int32_t* item_out /* [n_items*k] */, int32_t* count_out /* [n_items*k] */,
                  int32_t* n_out /* [n_items] */);
 
+/* ---- a9 / f3: kNN neighbourhood provider (north_star part 1; NO reference symbol exists) ----------
+ * user-user co-occurrence counts on the binarised ratings (int8 tcgen05 GEMM in row blocks) and, per
+ * user id, the k users sharing most items (self excluded, ties by ascending user id, users with no
+ * common item omitted).  Checked against an integer CPU restatement only; not used by fy_rm2_run, whose
+ * neighbourhood is the reference's: the user's cluster (M/rm/AbstractRM2Reducer.java:215-216). */
+int fy_knn_neighbours(fy_rm2_ctx* ctx, int32_t n_user_ids, int32_t n_items, int32_t k,
+                      int32_t* neighbour_out /* [n_user_ids*k], -1 padded */, int32_t* count_out /* may be NULL */,
+                      int32_t* n_out /* [n_user_ids], may be NULL */, double* ms_gemm_out /* may be NULL */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,10 +12,10 @@ from oracle import rm2_oracle as orc
 pytestmark = pytest.mark.gpu
 
 
-def _topk_ref(C, k):
+def _topk_ref(C, k, rows=None):
     n = C.shape[0]
     items = -np.ones((n, k), np.int32); counts = np.zeros((n, k), np.int32); cnt = np.zeros(n, np.int32)
-    for i in range(n):
+    for i in (range(n) if rows is None else rows):
         row = C[i].astype(np.int64).copy()
         row[i] = 0                                        # excludeSelfSimilarity
         nz = np.flatnonzero(row > 0)
@@ -48,3 +48,20 @@ def test_nonpositive_scores_and_duplicates_are_binarised():
         eng.set_ratings(user, item, score)
         got, _ = eng.cooc_counts(3, 3)
     assert got.tolist() == [[2, 2, 0], [2, 2, 0], [0, 0, 0]]
+
+
+@pytest.mark.parametrize("shape", ["tiny", "small", "ml-1m"])
+def test_knn_neighbours_match_integer_restatement(shape):
+    # a9 / f3: no reference symbol exists; the check is numpy's exact integer B B^T + (count desc, id asc) top-k
+    r = datagen.generate(shape)
+    n_u, n_i, k = r.n_users + 1, r.n_items + 1, 20
+    B = np.zeros((n_u, n_i), np.int32)
+    B[r.user, r.item] = 1
+    Cuu = B @ B.T
+    rows = np.arange(n_u) if n_u <= 1000 else np.random.default_rng(1).choice(n_u, 600, replace=False)
+    wi, wc, wn = _topk_ref(Cuu, k, rows)
+    with fy.Rm2Engine(number_of_items=r.n_items) as eng:
+        eng.set_ratings(r.user, r.item, r.score)
+        nb, cnt, n, ms = eng.knn_neighbours(n_u, n_i, k)
+    assert np.array_equal(n[rows], wn[rows]) and np.array_equal(nb[rows], wi[rows]) and np.array_equal(cnt[rows], wc[rows])
+    assert np.array_equal(n, np.minimum(k, (Cuu > 0).sum(1) - (Cuu.diagonal() > 0)))      # every row: neighbour count
