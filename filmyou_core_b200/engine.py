@@ -18,7 +18,7 @@ _LIB = None
 STATUS = {
     0: "FY_OK", -1: "FY_E_ARG", -2: "FY_E_USER_WITHOUT_RATING", -3: "FY_E_DUPLICATE_RATING",
     -4: "FY_E_CLUSTER_SIZE", -5: "FY_E_UNKNOWN_USER", -6: "FY_E_NOMEM", -7: "FY_E_CUDA",
-    -8: "FY_E_STATE", -9: "FY_E_UNSUPPORTED",
+    -8: "FY_E_STATE", -9: "FY_E_UNSUPPORTED", -10: "FY_E_ITEM_WITHOUT_RATING",
 }
 
 # every symbol include/filmyou_rm2.h declares
@@ -33,6 +33,12 @@ SEQ_EXPORTS = [
     "fy_seq_last_error", "fy_free", "fy_seq_write_intpair_float", "fy_seq_write_int_int", "fy_seq_write_int_double",
     "fy_mapfile_write_int_double", "fy_seq_read_intpair_float", "fy_seq_read_int_int", "fy_seq_read_int_double",
     "fy_rm2_run_files",
+]
+# include/filmyou_nmf.h
+NMF_EXPORTS = [
+    "fy_nmf_default_params", "fy_nmf_create", "fy_nmf_destroy", "fy_nmf_last_error", "fy_nmf_set_ratings",
+    "fy_nmf_set_factors", "fy_nmf_init_random", "fy_nmf_run", "fy_nmf_get_factors", "fy_nmf_cluster_assignment",
+    "fy_nmf_get_profile",
 ]
 
 
@@ -73,7 +79,7 @@ def sources():
 def build_library(force=False, verbose=False):
     """nvcc cross-compiles for sm_100a without a GPU (seconds)."""
     deps = sources() + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh")]
-    deps += [os.path.join(_HERE, "..", "include", h) for h in ("filmyou_rm2.h", "filmyou_seqfile.h")]
+    deps += [os.path.join(_HERE, "..", "include", h) for h in ("filmyou_rm2.h", "filmyou_seqfile.h", "filmyou_nmf.h")]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(d) <= os.path.getmtime(_SO) for d in deps):
         return _SO
     cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

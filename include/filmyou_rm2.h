@@ -58,7 +58,8 @@ typedef enum fy_status {
     FY_E_NOMEM = -6,                /* host or device allocation failed                              */
     FY_E_CUDA = -7,                 /* no device / CUDA runtime error (see fy_rm2_last_error)        */
     FY_E_STATE = -8,                /* call order violated (e.g. run before set_ratings)             */
-    FY_E_UNSUPPORTED = -9           /* parameter combination not implemented                         */
+    FY_E_UNSUPPORTED = -9,          /* parameter combination not implemented                         */
+    FY_E_ITEM_WITHOUT_RATING = -10  /* filmyou_nmf.h: an item no user rated (WComputationMapper.java:95-98) */
 } fy_status;
 
 /* Same names / meaning as the reference's Configuration keys

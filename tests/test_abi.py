@@ -20,12 +20,13 @@ def _declared(header="filmyou_rm2.h"):
 def test_header_and_binding_list_the_same_symbols():
     assert _declared() == sorted(engine.EXPORTS)
     assert _declared("filmyou_seqfile.h") == sorted(engine.SEQ_EXPORTS)
+    assert _declared("filmyou_nmf.h") == sorted(engine.NMF_EXPORTS)
 
 
 def test_library_builds_and_exports_every_declared_symbol():
     fy.build_library()
     L = fy.load_library()
-    for name in _declared() + _declared("filmyou_seqfile.h"):
+    for name in _declared() + _declared("filmyou_seqfile.h") + _declared("filmyou_nmf.h"):
         assert hasattr(L, name), name
     assert L.fy_rm2_abi_version() == 2
 
