@@ -37,7 +37,10 @@ constexpr int SCORE_THREADS = 128;
 constexpr int SCORE_CHUNK = 512;    // rated items staged in shared memory at a time
 constexpr int SCOREH_TILE = 512;    // candidates per CTA of the hi-word score kernel (4 per thread)
 constexpr int REFINE_THREADS = 256;
-constexpr int H_SLICE = 512;        // columns of one H row built by one warp (4 KB of doubles)
+#ifndef FY_H_SLICE_COLS
+#define FY_H_SLICE_COLS 512
+#endif
+constexpr int H_SLICE = FY_H_SLICE_COLS;   // columns of one H row built by one warp (4 KB of doubles)
 constexpr int H_THREADS = 256;
 constexpr int H_WARPS = H_THREADS / 32;   // 8 independent (row, slice) tasks per CTA
 constexpr int TOPN_THREADS = 512;

@@ -20,6 +20,7 @@
 //   sync   : int32 -1 | 16-byte sync marker, written before a record once 2000 bytes have passed
 //   Text   : Hadoop VInt length + UTF-8 bytes
 #include "../../include/filmyou_rm2.h"
+#include "../../include/filmyou_nmf.h"
 
 #include <dirent.h>
 #include <sys/stat.h>
@@ -39,6 +40,7 @@ const char* K_INT = "org.apache.hadoop.io.IntWritable";
 const char* K_FLOAT = "org.apache.hadoop.io.FloatWritable";
 const char* K_DOUBLE = "org.apache.hadoop.io.DoubleWritable";
 const char* K_LONG = "org.apache.hadoop.io.LongWritable";
+const char* K_VECTOR = "org.apache.mahout.math.VectorWritable";
 const int SYNC_INTERVAL = 100 * (4 + 16);      // SequenceFile.SYNC_INTERVAL
 
 thread_local char g_err[512] = {0};
@@ -416,5 +418,177 @@ extern "C" int fy_rm2_run_files(fy_rm2_ctx* ctx, const char* input_dir, const ch
         }
     }
     free(ru); free(ri); free(rs); free(cu); free(cc); free(sk); free(sv);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SequenceFile<IntWritable, VectorWritable>: the H and W factor matrices of the NMF / PPC step
+// (M/util/DataInitialization.java:76-88,120-131 write them, M/nmf/common/AbstractJoinVectorMapper.java:66-76
+// and every *ComputationReducer read them).  Mahout 0.8 VectorWritable (un-vendored dependency,
+// org.apache.mahout:mahout-core:0.8), restated from its published format -- PARITY UNPINNED at the byte level:
+//   byte flags  (0x01 dense | 0x02 sequential access | 0x04 named | 0x08 lax precision = floats)
+//   unsigned varint size           (7 bits per byte, least significant group first, 0x80 = more)
+//   dense : size doubles (big-endian) ;  sparse : varint nnz, then (varint index or index delta, double) pairs
+//   named : DataOutput.writeUTF name after the elements
+// The writer emits DenseVector records (flags 0x03), which is what DataInitialization and the reducers
+// (Vector.times / plus on dense vectors) produce.
+// ---------------------------------------------------------------------------------------------
+namespace {
+void put_uvarint(std::vector<uint8_t>& o, uint32_t v) {
+    while (v >= 0x80) { o.push_back((uint8_t)((v & 0x7f) | 0x80)); v >>= 7; }
+    o.push_back((uint8_t)v);
+}
+bool get_uvarint(const uint8_t*& p, const uint8_t* end, uint32_t& out) {
+    uint32_t v = 0;
+    for (int shift = 0; shift < 35; shift += 7) {
+        if (p >= end) return false;
+        const uint8_t b = *p++;
+        v |= (uint32_t)(b & 0x7f) << shift;
+        if (!(b & 0x80)) { out = v; return true; }
+    }
+    return false;
+}
+}  // namespace
+
+extern "C" int fy_seq_write_int_vector(const char* path, const int32_t* key, const double* rows, int64_t n, int32_t cols) {
+    if (!path || n < 0 || cols <= 0 || (n > 0 && (!key || !rows))) return fail(FY_E_ARG, "bad argument");
+    Writer w(K_INT, K_VECTOR, (uint64_t)n * 31 + (uint64_t)cols);
+    std::vector<uint8_t> val;
+    for (int64_t k = 0; k < n; k++) {
+        uint8_t kb[4];
+        for (int s = 0; s < 4; s++) kb[s] = (uint8_t)((uint32_t)key[k] >> (24 - 8 * s));
+        val.clear();
+        val.push_back(0x03);                                  // FLAG_DENSE | FLAG_SEQUENTIAL
+        put_uvarint(val, (uint32_t)cols);
+        for (int32_t c = 0; c < cols; c++) {
+            uint64_t bits;
+            memcpy(&bits, &rows[(size_t)k * cols + c], 8);
+            put_be64(val, bits);
+        }
+        w.append(kb, 4, val.data(), (int)val.size());
+    }
+    return w.flush(path);
+}
+
+// rows come back row-major [n x cols] in file order; every vector must have the same size
+extern "C" int fy_seq_read_int_vector(const char* path, int32_t** key, double** rows, int64_t* n, int32_t* cols) {
+    if (!path || !key || !rows || !n || !cols) return fail(FY_E_ARG, "bad argument");
+    std::vector<std::string> files;
+    int rc = list_files(path, files);
+    if (rc != FY_OK) return rc;
+    std::vector<int32_t> ks;
+    std::vector<double> vs;
+    int32_t width = -1;
+    for (const std::string& f : files) {
+        rc = scan_file(f, K_INT, K_VECTOR, [&](const uint8_t* k, int klen, const uint8_t* v, int vlen) -> int {
+            if (klen != 4 || vlen < 2) return fail(FY_E_ARG, "%s: bad <IntWritable, VectorWritable> record", f.c_str());
+            const uint8_t* p = v; const uint8_t* end = v + vlen;
+            const uint8_t flags = *p++;
+            if (flags >> 4) return fail(FY_E_ARG, "%s: unknown VectorWritable flags", f.c_str());
+            const bool dense = flags & 1, sequential = flags & 2, lax = flags & 8;
+            uint32_t size = 0;
+            if (!get_uvarint(p, end, size)) return fail(FY_E_ARG, "%s: truncated VectorWritable", f.c_str());
+            if (width < 0) width = (int32_t)size;
+            if ((int32_t)size != width) return fail(FY_E_ARG, "%s: vectors of different sizes", f.c_str());
+            const size_t base = vs.size();
+            vs.resize(base + size, 0.0);
+            auto element = [&](double& out) -> bool {
+                if (lax) { if (p + 4 > end) return false; const uint32_t b = get_be32(p); p += 4; float x; memcpy(&x, &b, 4); out = x; }
+                else { if (p + 8 > end) return false; const uint64_t b = get_be64(p); p += 8; memcpy(&out, &b, 8); }
+                return true;
+            };
+            if (dense) {
+                for (uint32_t c = 0; c < size; c++) if (!element(vs[base + c])) return fail(FY_E_ARG, "%s: truncated VectorWritable", f.c_str());
+            } else {
+                uint32_t nnz = 0, last = 0;
+                if (!get_uvarint(p, end, nnz)) return fail(FY_E_ARG, "%s: truncated VectorWritable", f.c_str());
+                for (uint32_t e = 0; e < nnz; e++) {
+                    uint32_t idx = 0; double x = 0;
+                    if (!get_uvarint(p, end, idx)) return fail(FY_E_ARG, "%s: truncated VectorWritable", f.c_str());
+                    if (sequential) { idx += last; last = idx; }
+                    if (idx >= size || !element(x)) return fail(FY_E_ARG, "%s: corrupt sparse VectorWritable", f.c_str());
+                    vs[base + idx] = x;
+                }
+            }
+            ks.push_back((int32_t)get_be32(k));
+            return FY_OK;
+        });
+        if (rc != FY_OK) return rc;
+    }
+    *n = (int64_t)ks.size();
+    *cols = width < 0 ? 0 : width;
+    *key = dup_vec(ks); *rows = dup_vec(vs);
+    if (!*key || !*rows) { free(*key); free(*rows); *key = nullptr; *rows = nullptr; return fail(FY_E_NOMEM, "out of memory"); }
+    return FY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// AbstractNMFDriver.run + ClusterAssignmentJob + CountClustersJob at the file level
+// (M/nmf/AbstractNMFDriver.java:92-141, M/nmf/clustering/ClusterAssignmentJob.java:47-95,
+//  M/nmf/clustering/CountClustersJob.java:41-80): read the ratings directory and the H / W files named by the
+// "H" / "W" options (or start from createInitialMatrices when h_in is NULL), iterate on the GPU, and leave
+// H, W, `clustering` and `clusteringCount` where the reference's jobs leave them.
+// ---------------------------------------------------------------------------------------------
+extern "C" int fy_nmf_run_files(fy_nmf_ctx* ctx, const fy_nmf_params* prm, const char* input_dir, const char* h_in, const char* w_in,
+                                uint64_t seed, const char* h_out, const char* w_out, const char* clustering_out,
+                                const char* clustering_count_out) {
+    if (!ctx || !prm || !input_dir || (!h_in) != (!w_in)) return fail(FY_E_ARG, "bad argument");
+    const int32_t U = prm->number_of_users, M = prm->number_of_items, k = prm->number_of_clusters, base = prm->id_base;
+    int32_t *ru = nullptr, *ri = nullptr, *hk = nullptr, *wk = nullptr;
+    float* rs = nullptr;
+    double *hv = nullptr, *wv = nullptr;
+    int64_t nnz = 0, hn = 0, wn = 0;
+    int32_t hc = 0, wc = 0;
+    auto engine_rc = [&](int rc, const char* what) { if (rc != FY_OK) fail(rc, "%s: %s", what, fy_nmf_last_error(ctx)); return rc; };
+    int rc = fy_seq_read_intpair_float(input_dir, &ru, &ri, &rs, &nnz);
+    if (rc == FY_OK) rc = engine_rc(fy_nmf_set_ratings(ctx, ru, ri, rs, nnz), "ratings");
+    if (rc == FY_OK && h_in) {
+        rc = fy_seq_read_int_vector(h_in, &hk, &hv, &hn, &hc);
+        if (rc == FY_OK) rc = fy_seq_read_int_vector(w_in, &wk, &wv, &wn, &wc);
+        if (rc == FY_OK && (hn != U || wn != M || hc != k || wc != k)) rc = fail(FY_E_ARG, "H / W do not have numberOfUsers / numberOfItems rows of numberOfClusters columns");
+        if (rc == FY_OK) {
+            std::vector<double> H((size_t)U * k), W((size_t)M * k);
+            std::vector<char> seen_h((size_t)U, 0), seen_w((size_t)M, 0);
+            for (int64_t r = 0; r < hn && rc == FY_OK; r++) {
+                const int64_t row = (int64_t)hk[r] - base;
+                if (row < 0 || row >= U || seen_h[row]) { rc = fail(FY_E_ARG, "H: row key outside the id range or repeated"); break; }
+                seen_h[row] = 1;
+                memcpy(&H[(size_t)row * k], &hv[(size_t)r * k], sizeof(double) * (size_t)k);
+            }
+            for (int64_t r = 0; r < wn && rc == FY_OK; r++) {
+                const int64_t row = (int64_t)wk[r] - base;
+                if (row < 0 || row >= M || seen_w[row]) { rc = fail(FY_E_ARG, "W: row key outside the id range or repeated"); break; }
+                seen_w[row] = 1;
+                memcpy(&W[(size_t)row * k], &wv[(size_t)r * k], sizeof(double) * (size_t)k);
+            }
+            if (rc == FY_OK) rc = engine_rc(fy_nmf_set_factors(ctx, H.data(), W.data()), "factors");
+        }
+    } else if (rc == FY_OK) {
+        rc = engine_rc(fy_nmf_init_random(ctx, seed), "createInitialMatrices");
+    }
+    if (rc == FY_OK) rc = engine_rc(fy_nmf_run(ctx), "PPCJob failed!");
+    if (rc == FY_OK && (h_out || w_out)) {
+        std::vector<double> H((size_t)U * k), W((size_t)M * k);
+        std::vector<int32_t> uk((size_t)U), ik((size_t)M);
+        for (int32_t r = 0; r < U; r++) uk[r] = base + r;
+        for (int32_t r = 0; r < M; r++) ik[r] = base + r;
+        rc = engine_rc(fy_nmf_get_factors(ctx, H.data(), W.data()), "factors");
+        if (rc == FY_OK && h_out) { rc = mkdirs(h_out); if (rc == FY_OK) rc = fy_seq_write_int_vector((std::string(h_out) + "/part-r-00000").c_str(), uk.data(), H.data(), U, k); }
+        if (rc == FY_OK && w_out) { rc = mkdirs(w_out); if (rc == FY_OK) rc = fy_seq_write_int_vector((std::string(w_out) + "/part-m-00000").c_str(), ik.data(), W.data(), M, k); }
+    }
+    if (rc == FY_OK && clustering_out) {
+        std::vector<int32_t> cl((size_t)U), cnt((size_t)k), uk((size_t)U);
+        for (int32_t r = 0; r < U; r++) uk[r] = base + r;
+        rc = engine_rc(fy_nmf_cluster_assignment(ctx, cl.data(), cnt.data()), "ClusterAssignmentJob failed!");
+        if (rc == FY_OK) rc = mkdirs(clustering_out);
+        if (rc == FY_OK) rc = fy_seq_write_int_int((std::string(clustering_out) + "/part-m-00000").c_str(), uk.data(), cl.data(), U);
+        if (rc == FY_OK && clustering_count_out) {
+            std::vector<int32_t> ck, cv;                      // CountReducer emits only the clusters that occur
+            for (int32_t c = 0; c < k; c++) if (cnt[c] > 0) { ck.push_back(c); cv.push_back(cnt[c]); }
+            rc = mkdirs(clustering_count_out);
+            if (rc == FY_OK) rc = fy_seq_write_int_int((std::string(clustering_count_out) + "/part-r-00000").c_str(), ck.data(), cv.data(), (int64_t)ck.size());
+        }
+    }
+    free(ru); free(ri); free(rs); free(hk); free(hv); free(wk); free(wv);
     return rc;
 }

@@ -32,7 +32,7 @@ EXPORTS = [
 SEQ_EXPORTS = [
     "fy_seq_last_error", "fy_free", "fy_seq_write_intpair_float", "fy_seq_write_int_int", "fy_seq_write_int_double",
     "fy_mapfile_write_int_double", "fy_seq_read_intpair_float", "fy_seq_read_int_int", "fy_seq_read_int_double",
-    "fy_rm2_run_files",
+    "fy_rm2_run_files", "fy_seq_write_int_vector", "fy_seq_read_int_vector", "fy_nmf_run_files",
 ]
 # include/filmyou_nmf.h
 NMF_EXPORTS = [
@@ -138,6 +138,9 @@ def load_library():
     L.fy_seq_read_int_int.argtypes = [C.c_char_p, C.POINTER(i32p), C.POINTER(i32p), C.POINTER(C.c_int64)]
     L.fy_seq_read_int_double.argtypes = [C.c_char_p, C.POINTER(i32p), C.POINTER(f64p), C.POINTER(C.c_int64)]
     L.fy_rm2_run_files.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, C.c_char_p]
+    L.fy_seq_write_int_vector.argtypes = [C.c_char_p, i32p, f64p, C.c_int64, C.c_int32]
+    L.fy_seq_read_int_vector.argtypes = [C.c_char_p, C.POINTER(i32p), C.POINTER(f64p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    L.fy_nmf_run_files.argtypes = [vp, vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]
     for name in EXPORTS + SEQ_EXPORTS:
         getattr(L, name)
     _LIB = L

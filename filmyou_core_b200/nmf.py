@@ -137,6 +137,15 @@ class NmfEngine:
         self._check(self._L.fy_nmf_cluster_assignment(self._h, _ptr(cl, C.c_int32), _ptr(cnt, C.c_int32)))
         return cl, cnt
 
+    def run_files(self, input_dir, h_in=None, w_in=None, seed=0, h_out=None, w_out=None, clustering_out=None,
+                  clustering_count_out=None):
+        """PPCDriver / NMFDriver + ClusterAssignmentJob + CountClustersJob at the file level (SequenceFiles in and out)."""
+        enc = lambda s: s.encode() if s else None
+        rc = self._L.fy_nmf_run_files(self._h, C.byref(self.params), enc(input_dir), enc(h_in), enc(w_in), C.c_uint64(seed),
+                                      enc(h_out), enc(w_out), enc(clustering_out), enc(clustering_count_out))
+        if rc != 0:
+            raise Rm2Error(rc, self._L.fy_seq_last_error().decode())
+
     def profile(self):
         p = NmfProfile()
         self._check(self._L.fy_nmf_get_profile(self._h, C.byref(p)))
@@ -158,3 +167,50 @@ def cluster_users(user, item, score, number_of_users, number_of_items, number_of
         cl, cnt = eng.cluster_assignment()
         ids = np.arange(number_of_users, dtype=np.int32) + eng.params.id_base
         return ids, cl, cnt
+
+
+def sub_cluster_ids(cluster, arg_max, number_of_users, number_of_clusters):
+    """ClusterAssignmentJob(true): k' = arg max(h_j) + cluster * ceil(numberOfUsers / numberOfClusters)
+    (M/nmf/clustering/FindSubClusterMapper.java:52-77)."""
+    stride = -(-int(number_of_users) // int(number_of_clusters))
+    return np.asarray(cluster, np.int64) * stride + np.asarray(arg_max, np.int64)
+
+
+def refine_clusters(user, item, score, ids, clustering, number_of_clusters, users_per_sub_cluster, number_of_iterations=10,
+                    seed=0, device=0, **kw):
+    """RMRecommenderDriver.clusterRefinement (M/rmrecommender/RMRecommenderDriver.java:217-266): for every cluster, renumber
+    its users and the items they rated densely (SubClusterMappingJob), run PPC on that sub-matrix with
+    ceil(users / usersPerSubCluster) columns from a random start, and give every user the id
+    cluster * ceil(numberOfUsers / numberOfClusters) + arg-max.  Returns (clustering', clusteringCount', sub-clusters made);
+    clusteringCount' is indexed by the new ids (0 for ids that do not occur).
+
+    The reference then sets numberOfClusters to the NUMBER of sub-clusters made (:262), smaller than the largest id it
+    has just written, so its RM2 job would index clusterSizes[] out of bounds (M/rm/AbstractRM2Reducer.java:93-105);
+    here the count array simply covers every id."""
+    user, item = np.asarray(user, np.int64), np.asarray(item, np.int64)
+    score = np.asarray(score, np.float32)
+    ids, clustering = np.asarray(ids, np.int64), np.asarray(clustering, np.int64)
+    keep = score > 0
+    user, item, score = user[keep], item[keep], score[keep]
+    order = np.argsort(ids)
+    cl_of_rating = clustering[order][np.searchsorted(ids[order], user)]
+    new_cl = np.empty(len(ids), np.int64)
+    made = 0
+    for c in range(int(number_of_clusters)):
+        members = np.sort(ids[clustering == c])
+        if len(members) == 0:
+            continue
+        sel = cl_of_rating == c
+        items_c, item_new = np.unique(item[sel], return_inverse=True)
+        user_new = np.searchsorted(members, user[sel])
+        sub = -(-len(members) // int(users_per_sub_cluster))
+        made += sub
+        with NmfEngine(PPC, len(members), len(items_c), sub, number_of_iterations, device=device, **kw) as eng:
+            eng.set_ratings(user_new + 1, item_new + 1, score[sel])
+            eng.init_random(seed + c)
+            eng.run()
+            arg_max, _ = eng.cluster_assignment()
+        new_cl[np.searchsorted(ids[order], members)] = sub_cluster_ids(c, arg_max, len(ids), number_of_clusters)
+    out = np.empty(len(ids), np.int64)
+    out[order] = new_cl
+    return out.astype(np.int32), np.bincount(out, minlength=int(out.max()) + 1).astype(np.int32), made

@@ -65,3 +65,20 @@ def read_int_double(path):
     a, b, n = C.POINTER(C.c_int32)(), C.POINTER(C.c_double)(), C.c_int64(0)
     _chk(L.fy_seq_read_int_double(path.encode(), C.byref(a), C.byref(b), C.byref(n)))
     return _take(a, n.value, np.int32), _take(b, n.value, np.float64)
+
+
+def write_int_vector(path, key, rows):
+    """SequenceFile<IntWritable, VectorWritable> of dense vectors: the H / W files (DataInitialization.java:113-138)."""
+    key, rows = _i32(key), np.ascontiguousarray(rows, dtype=np.float64)
+    assert rows.ndim == 2 and rows.shape[0] == len(key)
+    _chk(load_library().fy_seq_write_int_vector(path.encode(), _p(key, C.c_int32), _p(rows, C.c_double), len(key), rows.shape[1]))
+
+
+def read_int_vector(path):
+    """(keys, rows[n x cols]) in file order"""
+    L = load_library()
+    a, b, n, c = C.POINTER(C.c_int32)(), C.POINTER(C.c_double)(), C.c_int64(0), C.c_int32(0)
+    _chk(L.fy_seq_read_int_vector(path.encode(), C.byref(a), C.byref(b), C.byref(n), C.byref(c)))
+    keys = _take(a, n.value, np.int32)
+    rows = _take(b, n.value * c.value, np.float64).reshape(n.value, c.value)
+    return keys, rows

@@ -11,6 +11,8 @@
  *   fy_mapfile_write_int_double   rm2/itemColl, MapFile<IntWritable, DoubleWritable> (M/rm/RM2Job.java:190-196,
  *                           M/util/MapFileOutputFormat.java:171-178); read it back with fy_seq_read_int_double
  *   fy_rm2_run_files        RM2Job.run at the file level (M/rm/RM2Job.java:76-100)
+ *   fy_seq_*_int_vector     the H / W factor matrices, SequenceFile<IntWritable, VectorWritable> (Mahout 0.8)
+ *   fy_nmf_run_files        PPCDriver / NMFDriver + ClusterAssignmentJob + CountClustersJob at the file level
  *
  * A `path` may be one file or a directory (files starting with '_' or '.' are skipped, a MapFile
  * sub-directory contributes its `data` file), like M/util/HadoopUtils.java getSequenceReaders.
@@ -40,11 +42,27 @@ int fy_seq_read_intpair_float(const char* path, int32_t** first, int32_t** secon
 int fy_seq_read_int_int(const char* path, int32_t** key, int32_t** value, int64_t* n);
 int fy_seq_read_int_double(const char* path, int32_t** key, double** value, int64_t* n);
 
+/* H / W factor matrices, SequenceFile<IntWritable, VectorWritable> (M/util/DataInitialization.java:76-88,120-131).
+ * rows = [n x cols] row-major doubles in file order.  The writer emits Mahout 0.8 DenseVector records; the
+ * reader also accepts sparse / lax-precision vectors. */
+int fy_seq_write_int_vector(const char* path, const int32_t* key, const double* rows, int64_t n, int32_t cols);
+int fy_seq_read_int_vector(const char* path, int32_t** key, double** rows, int64_t* n, int32_t* cols);
+
 /* input_dir = mapred.input.dir, clustering_dir / clustering_count_dir = <directory>/<clustering>,
  * <directory>/<clusteringCount>, output_dir = mapred.output.dir, rm2_dir = <directory>/rm2 (may be NULL). */
 int fy_rm2_run_files(fy_rm2_ctx* ctx, const char* input_dir, const char* clustering_dir,
                      const char* clustering_count_dir, int32_t number_of_clusters,
                      const char* output_dir, const char* rm2_dir);
+
+/* AbstractNMFDriver.run + ClusterAssignmentJob + CountClustersJob at the file level (filmyou_nmf.h context; `prm`
+ * = the parameters the context was created with).  h_in / w_in = the "H" / "W" options (both NULL: random
+ * start from `seed`); any output path may be NULL.  Outputs: <h_out>/part-r-00000, <w_out>/part-m-00000,
+ * <clustering_out>/part-m-00000, <clustering_count_out>/part-r-00000. */
+struct fy_nmf_ctx;
+struct fy_nmf_params;
+int fy_nmf_run_files(struct fy_nmf_ctx* ctx, const struct fy_nmf_params* prm, const char* input_dir, const char* h_in,
+                     const char* w_in, uint64_t seed, const char* h_out, const char* w_out, const char* clustering_out,
+                     const char* clustering_count_out);
 
 #ifdef __cplusplus
 }

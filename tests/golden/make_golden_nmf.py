@@ -72,6 +72,19 @@ def main():
         "clustering": java_array(cl, "clustering"),
         "clusteringCount": java_array(cl, "clusteringCount"),
     }
+    # T/testdata/SubClusteringTestData.java:25-96: two clusters of 17 and 13 users, their H files (keys 1..17 and
+    # 18..30, T/nmf/clustering/TestClusterAssignment.java:79-82) and the expected sub-cluster ids
+    # cluster * ceil(numberOfUsers / numberOfClusters) + arg-max (M/nmf/clustering/FindSubClusterMapper.java:52-77)
+    sc = open(T + "testdata/SubClusteringTestData.java").read()
+    sc = sc.replace("double[][] H1 = {", "double[][] H1 = new double[][] {")
+    out["subClustering"] = {
+        "numberOfUsers": int(java_scalar(sc, "numberOfUsers")),
+        "numberOfClusters": int(java_scalar(sc, "numberOfClusters")),
+        "numberOfSubClusters": int(java_scalar(sc, "numberOfSubClusters")),
+        "H0": java_array(sc, "H0"),
+        "H1": java_array(sc, "H1"),
+        "clustering": java_array(sc, "clustering"),
+    }
     with open(os.path.join(HERE, "clustering_test_data.json"), "w") as f:
         json.dump(out, f, separators=(",", ":"))
     print("wrote clustering_test_data.json")

@@ -172,3 +172,74 @@ def test_clustering_chain_feeds_the_rm2_engine():
         got = eng.results()
     want = rm2.run(r.user, item, r.score, ids, clo, cnto, 0.1, M, 10)
     assert np.array_equal(got["user"], want["user"]) and np.array_equal(got["item"], want["item"])
+
+
+def test_file_level_driver_reads_and_writes_sequence_files(tmp_path):
+    """PPCHDFSDriverTest at the file level (T/nmf/ppc/PPCHDFSDriverTest.java:40-66): H, W and A SequenceFiles in, ten
+    iterations, H and W SequenceFiles out + ClusterAssignmentJob / CountClustersJob outputs."""
+    from filmyou_core_b200 import seqfile
+    g = _load("ppc_test_data.json")
+    u, i, s = orc.coo_from_dense(g["A"])
+    d = str(tmp_path)
+    os.makedirs(d + "/A")
+    seqfile.write_intpair_float(d + "/A/data", u, i, s)                                   # createIntPairFloatFile
+    seqfile.write_int_vector(d + "/H", np.arange(1, 31), np.array(g["H_init"]))          # createDoubleMatrix(..., "H", 1)
+    seqfile.write_int_vector(d + "/W", np.arange(1, 101), np.array(g["W_init"]))
+    with NmfEngine(PPC, 30, 100, 10, 10) as eng:
+        eng.run_files(d + "/A", d + "/H", d + "/W", h_out=d + "/H2", w_out=d + "/W2", clustering_out=d + "/clustering",
+                      clustering_count_out=d + "/clusteringCount")
+    hk, H = seqfile.read_int_vector(d + "/H2")
+    wk, W = seqfile.read_int_vector(d + "/W2")
+    assert hk.tolist() == list(range(1, 31)) and wk.tolist() == list(range(1, 101))
+    assert np.max(np.abs(H - np.array(g["H_ten"]))) < 1e-10 and np.max(np.abs(W - np.array(g["W_ten"]))) < 1e-10   # compareIntVectorData
+    ck, cv = seqfile.read_int_int(d + "/clustering")
+    cl, cnt = orc.cluster_assign(H)
+    assert ck.tolist() == list(range(1, 31)) and np.array_equal(cv, cl)
+    nk, nv = seqfile.read_int_int(d + "/clusteringCount")
+    assert nk.tolist() == np.flatnonzero(cnt).tolist() and nv.tolist() == cnt[cnt > 0].tolist()
+    with NmfEngine(PPC, 30, 100, 10, 3) as eng:                                          # random start, seeded
+        eng.run_files(d + "/A", seed=5, h_out=d + "/H3")
+        eng2_H = seqfile.read_int_vector(d + "/H3")[1]
+    with NmfEngine(PPC, 30, 100, 10, 3) as eng:
+        eng.set_ratings(u, i, s); eng.init_random(5); eng.run()
+        assert np.array_equal(eng.factors()[0], eng2_H)
+    with NmfEngine(PPC, 31, 100, 10, 1) as eng:                                          # H has 30 rows, not numberOfUsers
+        with pytest.raises(fy.Rm2Error):
+            eng.run_files(d + "/A", d + "/H", d + "/W")
+
+
+def test_sub_cluster_assignment_golden():
+    """TestClusterAssignment.subClusteringTest (T/nmf/clustering/TestClusterAssignment.java:70-101)."""
+    from filmyou_core_b200.nmf import sub_cluster_ids
+    g = _load("clustering_test_data.json")["subClustering"]
+    got = []
+    for c, H in enumerate((g["H0"], g["H1"])):
+        H = np.array(H)
+        with NmfEngine(PPC, H.shape[0], 3, H.shape[1], 0) as eng:
+            eng.set_factors(H, np.ones((3, H.shape[1])))
+            arg_max, _ = eng.cluster_assignment()
+        got += sub_cluster_ids(c, arg_max, g["numberOfUsers"], g["numberOfClusters"]).tolist()
+    assert got == g["clustering"]
+
+
+def test_cluster_refinement_feeds_the_rm2_engine():
+    from filmyou_core_b200.nmf import refine_clusters
+    from oracle import rm2_oracle as rm2
+    r = datagen.generate("small")
+    item, M = _dense_items(r)
+    cl2, cnt2, made = refine_clusters(r.user, item, r.score, r.cl_user, r.cl_cluster, r.n_clusters, 20, 6, seed=3)
+    stride = -(-r.n_users // r.n_clusters)
+    assert np.array_equal(cl2 // stride, r.cl_cluster)                 # users stay inside their first-level cluster
+    assert made == sum(-(-int(n) // 20) for n in r.cluster_size) and cnt2.sum() == r.n_users
+    assert len(np.unique(cl2)) > r.n_clusters
+    cl3, _, _ = refine_clusters(r.user, item, r.score, r.cl_user, r.cl_cluster, r.n_clusters, 20, 6, seed=3)
+    assert np.array_equal(cl2, cl3)                                    # seeded, deterministic
+    if cnt2[cnt2 > 0].min() < 2:
+        return
+    with fy.Rm2Engine(lam=0.1, number_of_items=M, top_n=5) as eng:
+        eng.set_ratings(r.user, item, r.score)
+        eng.set_clustering(r.cl_user, cl2, cnt2)
+        eng.run()
+        got = eng.results()
+    want = rm2.run(r.user, item, r.score, r.cl_user, cl2, cnt2, 0.1, M, 5)
+    assert np.array_equal(got["user"], want["user"]) and np.array_equal(got["item"], want["item"])

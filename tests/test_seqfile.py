@@ -113,3 +113,51 @@ def test_rejects_what_it_cannot_read(tmp_path):
         seqfile.read_int_int(p + ".t")
     with pytest.raises(fy.Rm2Error):
         seqfile.read_int_int(str(tmp_path / "missing"))
+
+
+def _uvarint(v):
+    out = b""
+    while v >= 0x80:
+        out += bytes([(v & 0x7f) | 0x80]); v >>= 7
+    return out + bytes([v])
+
+
+def test_int_vector_byte_image_and_round_trip(tmp_path):
+    # what DataInitialization.createDoubleMatrix(conf, data, dir, "H", 1) appends: (IntWritable(i), VectorWritable(DenseVector))
+    # M/util/DataInitialization.java:127-131; Mahout 0.8 VectorWritable: flags 0x03 (dense | sequential), varint size, doubles
+    p = str(tmp_path / "H")
+    rows = np.array([[0.25, 0.75], [1e-12, 3.0]])
+    seqfile.write_int_vector(p, [1, 2], rows)
+    raw = open(p, "rb").read()
+    hdr_len = len(_header("org.apache.hadoop.io.IntWritable", "org.apache.mahout.math.VectorWritable", b"\x00" * 16))
+    want = _header("org.apache.hadoop.io.IntWritable", "org.apache.mahout.math.VectorWritable", raw[hdr_len - 16:hdr_len])
+    for k, r in zip((1, 2), rows):
+        val = b"\x03" + _uvarint(2) + struct.pack(">dd", *r)
+        want += struct.pack(">iii", 4 + len(val), 4, k) + val
+    assert raw == want
+    rng = np.random.default_rng(3)
+    big = rng.random((700, 200))                           # size 200 needs a two-byte varint; 1.6 KB records -> sync escapes
+    keys = rng.permutation(700).astype(np.int32) + 1
+    seqfile.write_int_vector(p + "2", keys, big)
+    k2, r2 = seqfile.read_int_vector(p + "2")
+    assert np.array_equal(k2, keys) and np.array_equal(r2, big)
+
+
+def test_int_vector_reader_accepts_sparse_and_lax_vectors(tmp_path):
+    hdr = _header("org.apache.hadoop.io.IntWritable", "org.apache.mahout.math.VectorWritable", bytes(range(16)))
+    recs = []
+    # SequentialAccessSparseVector (flags 0x02): varint nnz, then (index delta, double)
+    recs.append((5, b"\x02" + _uvarint(6) + _uvarint(2) + _uvarint(1) + struct.pack(">d", 1.5) + _uvarint(3) + struct.pack(">d", -2.0)))
+    # RandomAccessSparseVector (flags 0x00): plain indices
+    recs.append((6, b"\x00" + _uvarint(6) + _uvarint(2) + _uvarint(5) + struct.pack(">d", 7.0) + _uvarint(0) + struct.pack(">d", 8.0)))
+    # dense, lax precision (flags 0x09): floats
+    recs.append((7, b"\x09" + _uvarint(6) + struct.pack(">6f", 1, 2, 3, 4, 5, 6)))
+    body = b"".join(struct.pack(">iii", 4 + len(v), 4, k) + v for k, v in recs)
+    p = str(tmp_path / "V")
+    open(p, "wb").write(hdr + body)
+    k, r = seqfile.read_int_vector(p)
+    assert k.tolist() == [5, 6, 7]
+    assert r.tolist() == [[0, 1.5, 0, 0, -2.0, 0], [8.0, 0, 0, 0, 0, 7.0], [1, 2, 3, 4, 5, 6]]
+    open(p + "bad", "wb").write(hdr + struct.pack(">iii", 4 + 3, 4, 1) + b"\x13" + _uvarint(1) + b"\x00")
+    with pytest.raises(fy.Rm2Error):
+        seqfile.read_int_vector(p + "bad")
