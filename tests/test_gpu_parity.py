@@ -139,6 +139,34 @@ def test_ml20m_sampled_users_vs_oracle():
     assert tot == otot and np.array_equal(us, ous) and np.array_equal(ip, oip[:len(ip)])
 
 
+def test_netflix_shape_sampled_users_and_properties():
+    # BASELINE.json configs[4] shape (480 189 x 17 770, 100 M ratings, 50 clusters) on ONE GPU: the whole job, the
+    # literal CPU loop on a seeded sample of light users, and the size-independent properties over all users
+    r = datagen.generate("netflix")
+    got = gpu_run(r, 0.1, r.n_items, 100)
+    assert got["users_scored"] == r.n_users and len(got["user"]) == r.n_users * 100
+    n_u = np.bincount(r.user, minlength=r.n_users + 1)
+    rng = np.random.default_rng(40)
+    sample = rng.choice(np.flatnonzero((n_u >= 20) & (n_u <= 24)), size=4, replace=False).astype(np.int32)
+    want = cpu_run(r, 0.1, r.n_items, 100, only_users=sample)
+    g = by_user(got)
+    sub = {k: np.concatenate([np.full(len(g[int(u)][0]), int(u)) if k == "user" else
+                              (g[int(u)][0] if k == "item" else g[int(u)][1])
+                              for u in by_user(want)]) for k in ("user", "item", "score64")}
+    assert assert_parity(sub, want, REL, "netflix sample") < 1e-9
+    items = got["item"].reshape(r.n_users, 100); scores = got["score64"].reshape(r.n_users, 100)
+    assert np.all(np.diff(scores, axis=1) <= 0)
+    srt = np.sort(items, axis=1)
+    assert np.all(srt[:, 1:] != srt[:, :-1])                           # distinct per user
+    rated = set(zip(r.user[:200000].tolist(), r.item[:200000].tolist()))
+    users = got["user"].reshape(r.n_users, 100)[:, 0]
+    pos = {int(u): k for k, u in enumerate(users)}
+    assert not any(i in items[pos[u]] for u, i in list(rated)[:20000])   # never recommends a rated item
+    us, ip, tot = got["stats"]
+    ous, _, oip, otot = orc.stats(r.user, r.item, r.score, r.cl_user)
+    assert tot == otot and np.array_equal(us, ous) and np.array_equal(ip, oip[:len(ip)])
+
+
 def test_more_than_4096_recommendations_per_user():
     # min(numberOfRecommendations, items of the cluster) beyond the shared-memory select bound: the engine
     # switches to a whole-row stable segmented sort; everything a user has not rated is emitted, in order
