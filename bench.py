@@ -377,6 +377,14 @@ def main():
                 "stage_ms_per_step": {k: worst[k] / args.steps for k in ("ms_index", "ms_gram", "ms_score", "ms_topn", "ms_refine")},
                 "stages_overlap": "H build, score and top-N/refine run on three streams; stage times are per stream and overlap",
                 "exact_reruns": worst["exact_rerun"]}
+    # second kernel of the step, for the record: k_build_H writes the fp64 plane (+ the 4-byte plane in auto mode)
+    gram_bytes = sum(p["gram_bytes"] for p in profs) * (1.5 if hi else 1.0)
+    gram_ms = sum(p["ms_gram"] for p in profs)
+    roofline["secondary"] = {"kernel": "fy::k_build_H", "bound": "hbm", "unit": "GB/s",
+                             "achieved": gram_bytes / (gram_ms * 1e-3) / 1e9 if gram_ms > 0 else 0.0, "peak": peak,
+                             "frac": (gram_bytes / (gram_ms * 1e-3) / 1e9 / peak) if gram_ms > 0 else 0.0,
+                             "definition": "bytes of H written (12 B per element with the 4-byte plane, 8 B without) / time of "
+                                           "the H-build stream segments of rank 0 (CUDA events; the stage overlaps the score kernel)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload, "clocks": clocks, "e2e": e2e,
