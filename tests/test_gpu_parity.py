@@ -376,6 +376,16 @@ def test_cpp_host_mirror(tmp_path):
     recs = [l.split() for l in out if l.startswith("rec")]
     assert [(int(a[1]), int(a[2])) for a in recs] == list(zip(want["user"].tolist(), want["item"].tolist()))
     assert np.allclose([float(a[3]) for a in recs], want["score32"], rtol=0, atol=1e-5)
+    # include/filmyou_nmf_job.hpp: one PPC iteration + arg-max on the same toy, against the NMF oracle
+    from oracle import nmf_oracle as norc
+    H0 = np.array([0.2, 0.8, 0.6, 0.4, 0.5, 0.5, 0.9, 0.1, 0.3, 0.7]).reshape(5, 2)
+    W0 = np.array([0.7, 0.3, 0.4, 0.6, 0.1, 0.9]).reshape(3, 2)
+    Ho, _ = norc.run(norc.PPC, r.user, r.item, r.score, H0, W0, 1, combine_len=1024, split_rows=256)
+    H = np.array([float(l.split()[1]) for l in out if l.startswith("H ")]).reshape(5, 2)
+    assert np.array_equal(H, Ho)
+    cl, cnt = norc.cluster_assign(Ho)
+    assert [int(l.split()[1]) for l in out if l.startswith("cluster")] == cl.tolist()
+    assert [l for l in out if l.startswith("count")] == ["count %d %d" % tuple(cnt)]
 
 
 def test_file_level_job_reads_and_writes_sequence_files(golden, golden_ratings, tmp_path):
