@@ -377,6 +377,13 @@ def main():
                 "stage_ms_per_step": {k: worst[k] / args.steps for k in ("ms_index", "ms_gram", "ms_score", "ms_topn", "ms_refine")},
                 "stages_overlap": "H build, score and top-N/refine run on three streams; stage times are per stream and overlap",
                 "exact_reruns": worst["exact_rerun"]}
+    # The plane rows are served out of L2 (traffic << algorithmic bytes), so the unit that actually bounds this kernel is
+    # the L2 -> SM path: /opt/skills/guides/B300_MICROARCH.md measures a full-chip LTS throughput cap of ~6300 B/clk
+    # (same L2 on B200); at the SM clock sampled during the timed region that is the ceiling reported here.
+    if clocks and clocks.get("sm_mhz"):
+        cap = 6300.0 * clocks["sm_mhz"] * 1e6 / 1e9
+        roofline["l2"] = {"cap_bytes_per_clk": 6300, "sm_mhz": clocks["sm_mhz"], "cap": cap, "unit": "GB/s", "frac": achieved / cap,
+                          "source": "B300_MICROARCH.md 'LTS throughput cap ~6300 B/cyc full-chip'; achieved = the same algorithmic bytes / launch time"}
     # second kernel of the step, for the record: k_build_H writes the fp64 plane (+ the 4-byte plane in auto mode)
     gram_bytes = sum(p["gram_bytes"] for p in profs) * (1.5 if hi else 1.0)
     gram_ms = sum(p["ms_gram"] for p in profs)
