@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <numeric>
@@ -104,6 +105,8 @@ struct fy_rm2_ctx {
     DBuf<int32_t> cand[2], cand_cnt[2];
     DBuf<double> cand_score[2];
     DBuf<int> overflow;
+    DBuf<uint64_t> perm_keys[2];
+    DBuf<int32_t> perm_vals, perm;
     DBuf<uint64_t> sort_keys[2];
     DBuf<int32_t> sort_idx[2], seg_off;
     DBuf<unsigned char> sort_tmp;
@@ -582,6 +585,17 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
         LAUNCH(ctx, k_alpha_cuj, cdiv((int64_t)n_slots * 32, 256), 256, 0, ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, keys2, rank_bits,
                ctx->rank_cluster.p, ctx->cstart.p, ctx->csc_src.p, ctx->csc_delta.p, n_slots, ctx->c_alpha.p, ctx->csr_c.p,
                ctx->cbound.p);
+    // processing order of the score kernel inside a cluster: most active users first (LPT), so that the 60x-longer
+    // CTA of a heavy user never starts at the tail of the grid
+    {
+        ctx->perm_keys[0].need(U); ctx->perm_keys[1].need(U); ctx->perm_vals.need(U); ctx->perm.need(U);
+        LAUNCH(ctx, k_perm_keys, cdiv(U, 256), 256, 0, ctx->rowptr.p, ctx->rank_cluster.p, U, ctx->perm_keys[0].p, ctx->perm_vals.p);
+        size_t tmp = 0;
+        const int end_bit = std::min(64, 32 + bits_for((uint64_t)KC));
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->perm_keys[0].p, ctx->perm_keys[1].p, ctx->perm_vals.p, ctx->perm.p, U, 0, end_bit, st));
+        ctx->cub_tmp.need(tmp);
+        CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, ctx->perm_keys[0].p, ctx->perm_keys[1].p, ctx->perm_vals.p, ctx->perm.p, U, 0, end_bit, st));
+    }
     CK(cudaEventRecord(ev_index, st));
 
     // ---------------- exponent-peel period L from a lower bound on t ----------------
@@ -644,6 +658,8 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
             if (lf >= 2 && std::abs(sexp) < 1000) plan[c] = Plan{2, lf >= 4 ? 4 : 2, sexp, std::ldexp(1.0, sexp)};
         }
     }
+    const char* lpt_env = std::getenv("FY_SCORE_LPT");
+    const bool lpt_on = !(lpt_env && std::strcmp(lpt_env, "0") == 0);
     ctx->prof.bytes_per_term = use_hi ? 4.0 : 8.0;
     ctx->prof.score_kernel = 0;
     ctx->prof.exact_rerun = force_exact ? 1 : 0;
@@ -744,6 +760,8 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
         for (int32_t b0 = r0; b0 < r1; b0 += batch) {
             const int32_t nb = std::min(batch, r1 - b0);
             const dim3 grid(nb, use_hi ? ld / SCOREH_TILE : ld / SCORE_TILE);
+            // the LPT order is a permutation of the cluster's ranks: usable when this batch is the whole cluster
+            const int32_t* lpt = (lpt_on && b0 == cs && nb == ce - cs) ? ctx->perm.p : (const int32_t*)nullptr;
             if (s_used[sb]) CK(cudaStreamWaitEvent(sS, sFree[sb], 0));
             LAUNCH_ON(ctx, sS, k_init_ustat, cdiv(nb, 256), 256, 0, ctx->ustat[sb].p, nb);
             {
@@ -751,9 +769,9 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
                 if (use_hi) ctx->prof.score_kernel = std::max(ctx->prof.score_kernel, plan[c].mode);
                 if (use_hi && plan[c].mode == 2) {
                     if (plan[c].lf >= 4)
-                        LAUNCH_ON(ctx, sS, k_score_f32<4>, grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, plan[c].scale, plan[c].sexp, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p);
+                        LAUNCH_ON(ctx, sS, k_score_f32<4>, grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, plan[c].scale, plan[c].sexp, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p, lpt);
                     else
-                        LAUNCH_ON(ctx, sS, k_score_f32<2>, grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, plan[c].scale, plan[c].sexp, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p);
+                        LAUNCH_ON(ctx, sS, k_score_f32<2>, grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, plan[c].scale, plan[c].sexp, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p, lpt);
                 } else if (use_hi) {
                     switch (L) {
                         case 8: LAUNCH_ON(ctx, sS, k_score_hi<8>, grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p); break;

@@ -474,6 +474,16 @@ __global__ void k_alpha_cuj(const int32_t* __restrict__ c_start, const int32_t* 
     }
 }
 
+// sort key (cluster, most rated items first) of every user rank -> processing order of the score kernel
+__global__ void k_perm_keys(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rank_cluster, int32_t n_users,
+                            uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_users) return;
+    const uint32_t n = (uint32_t)(rowptr[r + 1] - rowptr[r]);
+    keys[r] = ((uint64_t)(uint32_t)rank_cluster[r] << 32) | (uint64_t)(0xffffffffu - n);
+    vals[r] = r;
+}
+
 // per-user work estimate n_u * I_c (for sharding) as double
 __global__ void k_user_work(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rank_cluster,
                             const int32_t* __restrict__ icount, int32_t n_users, double* __restrict__ work) {
@@ -858,12 +868,15 @@ __global__ void __launch_bounds__(SCORE_THREADS)
 k_score_f32(const uint32_t* __restrict__ Hf, int32_t I_c, int32_t ld, int32_t rank_begin, int32_t slot0,
             const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_loc,
             const double* __restrict__ csr_c, const double* __restrict__ c_b, double plane_scale, int32_t scale_exp,
-            double log_items, double log_K, double* __restrict__ scores, unsigned long long* __restrict__ ustat) {
+            double log_items, double log_K, double* __restrict__ scores, unsigned long long* __restrict__ ustat,
+            const int32_t* __restrict__ perm /* users of the batch, most active first (null = rank order) */) {
     __shared__ int32_t s_j[SCORE_CHUNK];
     __shared__ float s_c[SCORE_CHUNK];
     __shared__ unsigned s_rated[SCOREH_TILE / 32];
 
-    const int32_t rank = rank_begin + blockIdx.x;
+    // longest-processing-time-first: the CTA of a user with thousands of rated items must not start last
+    const int32_t bx = perm ? perm[rank_begin + blockIdx.x] - rank_begin : (int32_t)blockIdx.x;
+    const int32_t rank = rank_begin + bx;
     const int32_t tile0 = blockIdx.y * SCOREH_TILE;
     const int32_t i = tile0 + 4 * threadIdx.x;
     const int32_t e0 = rowptr[rank];
@@ -934,7 +947,7 @@ k_score_f32(const uint32_t* __restrict__ Hf, int32_t I_c, int32_t ld, int32_t ra
         if (((word >> ((d + q) & 31)) & 1u) || i + q >= I_c) s[q] = NANV;
         if (s[q] == s[q]) { const unsigned long long k = desc_key(s[q]); kmin = min(kmin, k); kmax = max(kmax, k); cnt++; }
     }
-    double* dst = scores + (size_t)blockIdx.x * ld + i;
+    double* dst = scores + (size_t)bx * ld + i;
     *reinterpret_cast<double2*>(dst) = make_double2(s[0], s[1]);
     *reinterpret_cast<double2*>(dst + 2) = make_double2(s[2], s[3]);
     for (int o = 16; o > 0; o >>= 1) {
@@ -943,7 +956,7 @@ k_score_f32(const uint32_t* __restrict__ Hf, int32_t I_c, int32_t ld, int32_t ra
         kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
     }
     if ((threadIdx.x & 31) == 0 && cnt > 0) {
-        unsigned long long* st = ustat + 3 * (size_t)blockIdx.x;
+        unsigned long long* st = ustat + 3 * (size_t)bx;
         atomicAdd(st, (unsigned long long)cnt);
         atomicMin(st + 1, kmin);
         atomicMax(st + 2, kmax);

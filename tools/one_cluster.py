@@ -12,8 +12,11 @@ r = datagen.generate("one-cluster", n_users=2770, n_items=26744, nnz=400_000, n_
 with fy.Rm2Engine(lam=0.1, number_of_items=r.n_items, top_n=100) as eng:
     eng.set_ratings(r.user, r.item, r.score)
     eng.set_clustering(r.cl_user, r.cl_cluster, r.cluster_size)
+    hist = []
     for _ in range(runs):
         eng.run()
-    p = eng.profile()
+        hist.append(eng.profile())
+    p = hist[-1]
     n = eng.result_count()
-print(json.dumps({"results": n, **p}))
+med = lambda k: float(np.median([h[k] for h in hist[1:] or hist]))
+print(json.dumps({"results": n, **p, "median_ms_score": med("ms_score"), "median_ms_gram": med("ms_gram"), "median_ms_total": med("ms_total")}))
