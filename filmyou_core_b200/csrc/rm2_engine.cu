@@ -811,14 +811,13 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
                 const size_t k = seg_begin(SEG_TOPN, sT);
                 LAUNCH_ON(ctx, sT, k_topn, nb, TOPN_THREADS, topn_smem, ctx->scores[sb].p, ctx->ustat[sb].p, I_c, ld, b0, slot0,
                           ctx->prm.top_n, out_stride, ctx->prm.filter_users, ctx->split, ctx->n_splits, ctx->rank_userid.p,
-                          ctx->c_item.p, b0 - ub, ctx->out_item.p, ctx->out_score.p, ctx->out_count.p);
+                          ctx->c_item.p, b0 - ub, ctx->out_item.p, ctx->out_score.p, ctx->out_count.p,
+                          ctx->rowptr.p, cap, plan[c].mode == 2 ? 2.5e-7 : 4.8e-7, use_hi ? ctx->cand[sb].p : (int32_t*)nullptr,
+                          use_hi ? ctx->cand_cnt[sb].p : (int32_t*)nullptr, ctx->overflow.p);
                 seg_end(k, sT);
             }
             if (use_hi) {
                 const size_t k = seg_begin(SEG_REFINE, sT);
-                LAUNCH_ON(ctx, sT, k_margin_gather, nb, 256, 0, ctx->scores[sb].p, I_c, ld, b0, ub, ctx->rowptr.p, out_stride,
-                          ctx->out_score.p, ctx->out_count.p, cap, plan[c].mode == 2 ? 2.5e-7 : 4.8e-7, ctx->cand[sb].p,
-                          ctx->cand_cnt[sb].p, ctx->overflow.p);
                 LAUNCH_ON(ctx, sT, k_refine_score, dim3(nb, cdiv(cap, REFINE_THREADS / 32)), REFINE_THREADS, 0, ctx->H[hb].p, ld, b0,
                           slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, log_items, log_K, cap, ctx->cand[sb].p,
                           ctx->cand_cnt[sb].p, ctx->cand_score[sb].p);
@@ -1109,7 +1108,8 @@ extern "C" int fy_knn_neighbours(fy_rm2_ctx* ctx, int32_t n_user_ids, int32_t n_
                 LAUNCH(ctx, k_cooc_scores, dim3(nb, ld / SCORE_TILE), SCORE_THREADS, 0, ctx->cooc_counts.p, U, ldc, ld, b0, r0,
                        ctx->scores[0].p, ctx->ustat[0].p);
                 LAUNCH(ctx, k_topn, nb, TOPN_THREADS, topn_smem, ctx->scores[0].p, ctx->ustat[0].p, U, ld, 0, 0, k, k, 0, 0, 1,
-                       ctx->cooc_zero.p, ctx->cooc_iota.p, r0 + b0, ctx->cooc_out_item.p, ctx->cooc_out_score.p, ctx->cooc_out_cnt.p);
+                       ctx->cooc_zero.p, ctx->cooc_iota.p, r0 + b0, ctx->cooc_out_item.p, ctx->cooc_out_score.p, ctx->cooc_out_cnt.p,
+                       (const int32_t*)nullptr, 0, 0.0, (int32_t*)nullptr, (int32_t*)nullptr, (int*)nullptr);
             }
         }
         int h_flags[DF_COUNT];
@@ -1161,7 +1161,8 @@ extern "C" int fy_cooc_topk(fy_rm2_ctx* ctx, int32_t k, int32_t* item_out, int32
             LAUNCH(ctx, k_cooc_scores, dim3(nb, ld / SCORE_TILE), SCORE_THREADS, 0, ctx->cooc_counts.p, n, ldc, ld, r0, 0,
                    ctx->scores[0].p, ctx->ustat[0].p);
             LAUNCH(ctx, k_topn, nb, TOPN_THREADS, topn_smem, ctx->scores[0].p, ctx->ustat[0].p, n, ld, 0, 0, k, k, 0, 0, 1,
-                   ctx->cooc_zero.p, ctx->cooc_iota.p, r0, ctx->cooc_out_item.p, ctx->cooc_out_score.p, ctx->cooc_out_cnt.p);
+                   ctx->cooc_zero.p, ctx->cooc_iota.p, r0, ctx->cooc_out_item.p, ctx->cooc_out_score.p, ctx->cooc_out_cnt.p,
+                   (const int32_t*)nullptr, 0, 0.0, (int32_t*)nullptr, (int32_t*)nullptr, (int*)nullptr);
         }
         std::vector<double> sc((size_t)n * k);
         std::vector<int32_t> cnt((size_t)n);

@@ -754,7 +754,7 @@ k_score(const double* __restrict__ H, int32_t I_c, int32_t ld, int32_t rank_begi
 // Approximate score kernel: identical to k_score but streams the hi-word plane of H (4 bytes per
 // log-term, 20-bit mantissa): CTA = (user, 512 candidates), 16-byte loads of 4 candidates.
 // |log t~ - log t| <= 2^-21 per term, so |score~ - score| <= n_u * 2^-21 (+ fp64 noise): a rigorous
-// bound that k_margin_gather turns into a candidate set containing the exact top-N; k_refine then
+// bound that k_topn's margin pass turns into a candidate set containing the exact top-N; k_refine then
 // re-scores those candidates from the fp64 plane.  Only used when every t > 0 (L >= 2).
 // ---------------------------------------------------------------------------------------------
 template <int L>
@@ -963,37 +963,6 @@ k_score_f32(const uint32_t* __restrict__ Hf, int32_t I_c, int32_t ld, int32_t ra
     }
 }
 
-// candidates that can be in the exact top-N: approximate score >= (N-th approximate score) - 2*eps
-__global__ void __launch_bounds__(256)
-k_margin_gather(const double* __restrict__ scores, int32_t I_c, int32_t ld, int32_t rank_begin, int32_t ub,
-                const int32_t* __restrict__ rowptr, int32_t out_stride, const double* __restrict__ out_score,
-                const int32_t* __restrict__ out_count, int32_t cap, double eps_per_term, int32_t* __restrict__ cand,
-                int32_t* __restrict__ cand_cnt, int* __restrict__ overflow) {
-    __shared__ int s_n;
-    const int32_t rank = rank_begin + blockIdx.x, orow = rank - ub;
-    const int32_t n_out = out_count[orow];
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    if (n_out > 0) {
-        const double n_u = (double)(rowptr[rank + 1] - rowptr[rank]);
-        const double eps = n_u * eps_per_term + 1e-9;              // rigorous per-term bound + fp64 slack
-        const double thr = out_score[(size_t)orow * out_stride + n_out - 1] - 2.0 * eps;
-        const double* __restrict__ row = scores + (size_t)blockIdx.x * ld;
-        for (int32_t i = threadIdx.x; i < I_c; i += blockDim.x) {
-            const double sc = row[i];
-            if (sc == sc && sc >= thr) {
-                const int pos = atomicAdd(&s_n, 1);
-                if (pos < cap) cand[(size_t)blockIdx.x * cap + pos] = i;
-            }
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        cand_cnt[blockIdx.x] = s_n;
-        if (s_n > cap) atomicAdd(overflow, 1);
-    }
-}
-
 // exact fp64 re-score of the candidates: grid (user, candidate group), one warp per candidate, lanes
 // stride the rated items (4 gathers in flight per lane); the lane products are combined by a fixed
 // butterfly, so the result is deterministic and identical item columns give identical scores.
@@ -1089,7 +1058,11 @@ k_topn(const double* __restrict__ scores, const unsigned long long* __restrict__
        int32_t top_n, int32_t out_stride, int32_t filter_users, int32_t split, int32_t n_splits,
        const int32_t* __restrict__ rank_userid, const int32_t* __restrict__ c_item,
        int32_t out_row0, int32_t* __restrict__ out_item, double* __restrict__ out_score,
-       int32_t* __restrict__ out_count) {
+       int32_t* __restrict__ out_count,
+       // optional (auto mode): the candidates that can be in the EXACT top-N, i.e. approximate score >= (N-th approximate
+       // score) - 2 eps, collected in one more pass over the row while it is still in L2 (was a kernel of its own)
+       const int32_t* __restrict__ rowptr, int32_t cap, double eps_per_term, int32_t* __restrict__ cand,
+       int32_t* __restrict__ cand_cnt, int* __restrict__ overflow) {
     extern __shared__ unsigned char smem_raw[];
     constexpr int RBITS = 11, NBINS = 1 << RBITS;             // 4 bins per thread
     static_assert(NBINS == 4 * TOPN_THREADS, "bucket search assumes 4 bins per thread");
@@ -1107,7 +1080,7 @@ k_topn(const double* __restrict__ scores, const unsigned long long* __restrict__
     const int n_out = min(top_n, c_u);
     // split filter :203-205, "no unrated item" :210-213, filterUsers :220-223
     if (uid < filter_users || (n_splits > 1 && (uid % n_splits) != split) || n_out == 0) {
-        if (tid == 0) out_count[orow] = 0;
+        if (tid == 0) { out_count[orow] = 0; if (cand_cnt) cand_cnt[blockIdx.x] = 0; }
         return;
     }
     const uint64_t kbase = ustat[3 * (size_t)blockIdx.x + 1];
@@ -1228,6 +1201,26 @@ k_topn(const double* __restrict__ scores, const unsigned long long* __restrict__
         out_score[(size_t)orow * out_stride + t] = key_to_score(sk[t]);
     }
     if (tid == 0) out_count[orow] = n_out;
+    if (cand) {
+        const double n_u = (double)(rowptr[rank + 1] - rowptr[rank]);
+        const double eps = n_u * eps_per_term + 1e-9;              // rigorous per-term bound + fp64 slack
+        const double thr = key_to_score(sk[n_out - 1]) - 2.0 * eps;
+        __syncthreads();                                           // everyone has read sk[n_out - 1]; s_nsel is free
+        if (tid == 0) s_nsel = 0;
+        __syncthreads();
+        for (int32_t i = tid; i < I_c; i += TOPN_THREADS) {
+            const double sc = row[i];
+            if (sc == sc && sc >= thr) {
+                const int pos = atomicAdd(&s_nsel, 1);
+                if (pos < cap) cand[(size_t)blockIdx.x * cap + pos] = i;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            cand_cnt[blockIdx.x] = s_nsel;
+            if (s_nsel > cap) atomicAdd(overflow, 1);
+        }
+    }
 }
 
 // ---- large-N path (min(N, I_c) > TOPN_MAX_SELECT): whole-row stable segmented sort ----
