@@ -48,6 +48,23 @@ def test_no_cpu_fallback():
     assert e.value.code == -7
 
 
+def test_no_cpu_fallback_for_the_clustering_step():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from filmyou_core_b200.nmf import PPC, NmfEngine
+    with pytest.raises(fy.Rm2Error) as e:
+        NmfEngine(PPC, 30, 100, 10)
+    assert e.value.code == -7
+    L = fy.load_library()
+    from filmyou_core_b200.nmf import NmfParams, _lib
+    _lib()
+    p = NmfParams()
+    L.fy_nmf_default_params(p)
+    # M/rmrecommender/RMRecommenderDriver.java:94,115 (numberOfIterations 10, normalizationFrequency 12); PPC is what the driver runs
+    assert (p.mode, p.number_of_iterations, p.normalization_frequency, p.apply_normalization, p.id_base) == (1, 10, 12, 0, 1)
+
+
 def test_product_package_never_touches_the_oracle():
     pkg = os.path.join(ROOT, "filmyou_core_b200")
     for d, _, files in os.walk(pkg):
