@@ -90,3 +90,25 @@ def test_missing_rows_fail_like_the_reference(ppc):
     with pytest.raises(orc.OracleError) as e:
         orc.run(orc.NMF, u[keep], i[keep], s[keep], g["H_init"], g["W_init"], 1)
     assert e.value.code == -10 and e.value.bad_id == 42
+
+
+def test_summation_structure_only_moves_the_last_bits(ppc):
+    """combiner group sizes change the summation tree, never the result beyond rounding (the reference's own order is
+    shuffle-defined); relabelling users and items permutes the factor rows accordingly."""
+    g = ppc
+    u, i, s = orc.coo_from_dense(g["A"])
+    base = orc.run(orc.PPC, u, i, s, g["H_init"], g["W_init"], 5)
+    for cl, sr in ((1, 1), (3, 7), (1024, 256)):
+        H, W = orc.run(orc.PPC, u, i, s, g["H_init"], g["W_init"], 5, combine_len=cl, split_rows=sr)
+        assert np.max(np.abs(H - base[0]) / np.abs(base[0])) < 1e-12 and np.max(np.abs(W - base[1]) / np.abs(base[1])) < 1e-12
+    rng = np.random.default_rng(0)
+    pu, pi = rng.permutation(30), rng.permutation(100)          # new id of old id k is p[k] + 1
+    H0 = np.empty((30, 10)); H0[pu] = np.array(g["H_init"])
+    W0 = np.empty((100, 10)); W0[pi] = np.array(g["W_init"])
+    Hp, Wp = orc.run(orc.PPC, pu[u - 1] + 1, pi[i - 1] + 1, s, H0, W0, 5)
+    assert np.max(np.abs(Hp[pu] - base[0]) / np.abs(base[0])) < 1e-12
+    assert np.max(np.abs(Wp[pi] - base[1]) / np.abs(base[1])) < 1e-12
+    # input order of the ratings is irrelevant (they are sorted by (row, column) first)
+    sh = rng.permutation(len(u))
+    Hs, Ws = orc.run(orc.PPC, u[sh], i[sh], s[sh], g["H_init"], g["W_init"], 5)
+    assert np.array_equal(Hs, base[0]) and np.array_equal(Ws, base[1])
