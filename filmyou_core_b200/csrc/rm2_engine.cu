@@ -73,7 +73,8 @@ struct fy_rm2_ctx {
     // clustering (host)
     int32_t n_users = 0, n_clusters = 0;
     std::vector<int32_t> h_rank_userid, h_rank_cluster, h_cstart, h_input_rank;  // input order -> rank
-    DBuf<int32_t> uid_sorted, uid_rank, rank_userid, rank_cluster, cstart;
+    DBuf<int32_t> uid_sorted, uid_rank, uid_table, rank_userid, rank_cluster, cstart;
+    int32_t uid_table_n = 0, uid_table_min = 0;      // direct user id -> rank table (dense ids), else binary search
 
     // fine-seam overrides (rank order / item id order), empty when unused
     DBuf<double> ext_usum, ext_iprob;
@@ -302,35 +303,62 @@ static int upload_clustering(fy_rm2_ctx* ctx, const int32_t* user, const int32_t
         for (int32_t c = 0; c < n_clusters; c++)
             if (cnt[c] != cluster_size[c])
                 return ctx->fail(FY_E_CLUSTER_SIZE, "clusteringCount[%d] = %d but %d users map to it", c, cluster_size[c], cnt[c]);
-    // users[] of the reducer, canonicalised: (cluster, user id) ascending
-    std::vector<int32_t> order((size_t)U);
-    std::iota(order.begin(), order.end(), 0);
-    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-        if (cluster[a] != cluster[b]) return cluster[a] < cluster[b];
-        return user[a] < user[b];
-    });
-    ctx->h_rank_userid.resize(U); ctx->h_rank_cluster.resize(U); ctx->h_input_rank.resize(U);
-    for (int32_t r = 0; r < U; r++) {
-        ctx->h_rank_userid[r] = user[order[r]];
-        ctx->h_rank_cluster[r] = cluster[order[r]];
-        ctx->h_input_rank[order[r]] = r;
-    }
+    // users[] of the reducer, canonicalised: (cluster, user id) ascending.  A stable counting sort by cluster
+    // (O(U)) leaves each cluster's users in input order; only segments whose ids are not already ascending
+    // (the `clustering` file is normally written by ascending user id) pay for a comparison sort.
     ctx->h_cstart.assign((size_t)n_clusters + 1, 0);
     for (int32_t c = 0; c < n_clusters; c++) ctx->h_cstart[c + 1] = ctx->h_cstart[c] + cnt[c];
-    // id -> rank lookup table sorted by id
-    std::vector<int32_t> by_id((size_t)U);
-    std::iota(by_id.begin(), by_id.end(), 0);
-    std::sort(by_id.begin(), by_id.end(), [&](int32_t a, int32_t b) { return ctx->h_rank_userid[a] < ctx->h_rank_userid[b]; });
-    std::vector<int32_t> ids((size_t)U), ranks((size_t)U);
-    for (int32_t k = 0; k < U; k++) { ids[k] = ctx->h_rank_userid[by_id[k]]; ranks[k] = by_id[k]; }
-    for (int32_t k = 1; k < U; k++)
-        if (ids[k] == ids[k - 1]) return ctx->fail(FY_E_ARG, "user %d appears twice in `clustering`", ids[k]);
+    std::vector<int32_t> order((size_t)U);
+    {
+        std::vector<int32_t> fill(ctx->h_cstart.begin(), ctx->h_cstart.end() - 1);
+        for (int32_t k = 0; k < U; k++) order[fill[cluster[k]]++] = k;
+        for (int32_t c = 0; c < n_clusters; c++) {
+            int32_t* b = order.data() + ctx->h_cstart[c]; int32_t* e = order.data() + ctx->h_cstart[c + 1];
+            bool sorted = true;
+            for (int32_t* q = b; q + 1 < e; q++) if (user[q[0]] >= user[q[1]]) { sorted = false; break; }
+            if (!sorted) std::sort(b, e, [&](int32_t a, int32_t bb) { return user[a] < user[bb]; });
+        }
+    }
+    ctx->h_rank_userid.resize(U); ctx->h_rank_cluster.resize(U); ctx->h_input_rank.resize(U);
+    int32_t uid_min = 0x7fffffff, uid_max = -0x7fffffff - 1;
+    for (int32_t r = 0; r < U; r++) {
+        const int32_t id = user[order[r]];
+        ctx->h_rank_userid[r] = id;
+        ctx->h_rank_cluster[r] = cluster[order[r]];
+        ctx->h_input_rank[order[r]] = r;
+        uid_min = std::min(uid_min, id); uid_max = std::max(uid_max, id);
+    }
     CK(cudaSetDevice(ctx->prm.device));
-    ctx->uid_sorted.need(U); ctx->uid_rank.need(U); ctx->rank_userid.need(U); ctx->rank_cluster.need(U);
-    ctx->cstart.need((size_t)n_clusters + 1);
     cudaStream_t st = ctx->stream;
-    CK(cudaMemcpyAsync(ctx->uid_sorted.p, ids.data(), (size_t)U * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->uid_rank.p, ranks.data(), (size_t)U * 4, cudaMemcpyHostToDevice, st));
+    // user id -> rank: a direct table when the ids are dense enough (one load per rating in k_make_keys), else
+    // the id-sorted arrays that k_make_keys binary-searches
+    std::vector<int32_t> ids, ranks, table;
+    const int64_t span = (int64_t)uid_max - (int64_t)uid_min + 1;
+    ctx->uid_table_n = 0; ctx->uid_table_min = 0;
+    if (uid_min >= 0 && span <= 8ll * U + (1ll << 20)) {
+        table.assign((size_t)span, -1);
+        for (int32_t r = 0; r < U; r++) {
+            int32_t& slot = table[(size_t)(ctx->h_rank_userid[r] - uid_min)];
+            if (slot >= 0) return ctx->fail(FY_E_ARG, "user %d appears twice in `clustering`", ctx->h_rank_userid[r]);
+            slot = r;
+        }
+        ctx->uid_table.need((size_t)span);
+        CK(cudaMemcpyAsync(ctx->uid_table.p, table.data(), (size_t)span * 4, cudaMemcpyHostToDevice, st));
+        ctx->uid_table_n = (int32_t)span; ctx->uid_table_min = uid_min;
+    } else {
+        std::vector<int32_t> by_id((size_t)U);
+        std::iota(by_id.begin(), by_id.end(), 0);
+        std::sort(by_id.begin(), by_id.end(), [&](int32_t a, int32_t b) { return ctx->h_rank_userid[a] < ctx->h_rank_userid[b]; });
+        ids.resize((size_t)U); ranks.resize((size_t)U);
+        for (int32_t k = 0; k < U; k++) { ids[k] = ctx->h_rank_userid[by_id[k]]; ranks[k] = by_id[k]; }
+        for (int32_t k = 1; k < U; k++)
+            if (ids[k] == ids[k - 1]) return ctx->fail(FY_E_ARG, "user %d appears twice in `clustering`", ids[k]);
+        ctx->uid_sorted.need(U); ctx->uid_rank.need(U);
+        CK(cudaMemcpyAsync(ctx->uid_sorted.p, ids.data(), (size_t)U * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->uid_rank.p, ranks.data(), (size_t)U * 4, cudaMemcpyHostToDevice, st));
+    }
+    ctx->rank_userid.need(U); ctx->rank_cluster.need(U);
+    ctx->cstart.need((size_t)n_clusters + 1);
     CK(cudaMemcpyAsync(ctx->rank_userid.p, ctx->h_rank_userid.data(), (size_t)U * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->rank_cluster.p, ctx->h_rank_cluster.data(), (size_t)U * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->cstart.p, ctx->h_cstart.data(), ((size_t)n_clusters + 1) * 4, cudaMemcpyHostToDevice, st));
@@ -393,7 +421,8 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     ctx->icount.need(KC); ctx->item_off.need((size_t)KC + 1);
     ctx->tstart.need(tab);
     LAUNCH(ctx, k_make_keys, cdiv(nnz, 256), 256, 0, ctx->in_user.p, ctx->in_item.p, ctx->in_score.p, nnz,
-           ctx->uid_sorted.p, ctx->uid_rank.p, U, item_bits, ctx->max_item, ctx->keys_a.p, ctx->counters.p, ctx->flags.p);
+           ctx->uid_sorted.p, ctx->uid_rank.p, U, ctx->uid_table_n ? ctx->uid_table.p : (const int32_t*)nullptr, ctx->uid_table_n,
+           ctx->uid_table_min, item_bits, ctx->max_item, ctx->keys_a.p, ctx->counters.p, ctx->flags.p);
     unsigned long long h_counters[2]; int h_flags[DF_COUNT];
     // Sharded index: with exact (dyadic) scores the global statistics need no sort, so each rank sorts and
     // indexes only the ratings of the clusters it touches (~1/N of them) instead of all of them.
@@ -687,12 +716,76 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     auto seg_begin = [&](int kind, cudaStream_t strm) { CK(cudaEventRecord(ctx->ev(evi), strm)); segs.push_back(Seg{kind, evi, 0}); evi++; return segs.size() - 1; };
     auto seg_end = [&](size_t k, cudaStream_t strm) { CK(cudaEventRecord(ctx->ev(evi), strm)); segs[k].e1 = evi; evi++; };
     const size_t SCORE_BUF_BYTES = big_n ? ((size_t)1 << 29) : ((size_t)2 << 30);
+    // H-build variant: 2 (default) = k_build_H2 (warp per (row, wide column range), rater-sequential, cp.async ring);
+    // 1 = the round-1 flattened-list kernel (kept for A/B: FY_BUILD_H=1).  FY_H2_CFG picks the (range, warps, depth) instance.
+    const char* bh_env = std::getenv("FY_BUILD_H");
+    const int build_variant = (bh_env && std::strcmp(bh_env, "1") == 0) ? 1 : 2;
+    const char* h2_env = std::getenv("FY_H2_CFG");
+    const int h2_cfg = h2_env ? std::atoi(h2_env) : 0;
+    const char* h2_order_env = std::getenv("FY_H2_ORDER");
+    const char* h2_bulk_env = std::getenv("FY_H2_BULK");
+    const bool h2_bulk = !(h2_bulk_env && std::strcmp(h2_bulk_env, "0") == 0);
+    int32_t h2_rw = 1536, h2_nw = 2;                 // measured best of the instances below at ML-20M and Netflix shape
+    switch (h2_cfg) {
+        case 1: h2_rw = 2048; h2_nw = 2; break;
+        case 2: h2_rw = 512; h2_nw = 8; break;
+        case 3: h2_rw = 1024; h2_nw = 4; break;
+        case 4: h2_rw = 768; h2_nw = 4; break;
+        case 5: h2_rw = 1024; h2_nw = 2; break;
+        default: break;
+    }
     auto h_geometry = [&](int32_t I_c, int32_t& ld, int32_t& slice_w, int32_t& chunk_w, int32_t& nchunk, int32_t& n_bound) {
         ld = cdiv(I_c, SCOREH_TILE) * SCOREH_TILE;
+        if (build_variant == 2) {
+            slice_w = h2_rw;
+            chunk_w = h2_rw * h2_nw;
+            nchunk = cdiv(cdiv(I_c, h2_rw), h2_nw);
+            n_bound = cdiv(I_c, h2_rw) + 1;
+            return;
+        }
         slice_w = H_SLICE;
         chunk_w = H_SLICE * H_WARPS;
         nchunk = cdiv(cdiv(I_c, H_SLICE), H_WARPS);     // CTAs per row
         n_bound = cdiv(I_c, H_SLICE) + 1;               // slice boundaries per user
+    };
+    auto launch_build = [&](cudaStream_t strm, int32_t I_c, int32_t ld, int32_t nchunk, int32_t n_bound, int32_t slot0,
+                            const int32_t* cp, double* Hp, uint32_t* Hhp, int mode, double scale) {
+#define FY_H2_LAUNCH_B(RW, NW, PM, BK)                                                                                \
+        do {                                                                                                          \
+            const size_t smem = (size_t)(NW) * (RW) * 8;                                                              \
+            CK(cudaFuncSetAttribute(k_build_H2<RW, NW, PM, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            const bool rowmaj = !(h2_order_env && std::strcmp(h2_order_env, "0") == 0);                              \
+            LAUNCH_ON(ctx, strm, (k_build_H2<RW, NW, PM, BK>), rowmaj ? dim3((unsigned)I_c * (unsigned)nchunk) : dim3(I_c, nchunk), (NW) * 32, smem, I_c, ld, n_bound - 1, slot0,  \
+                      ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, ctx->c_alpha.p, ctx->csc_lu.p, ctx->csc_delta.p, cp,  \
+                      ctx->csr_loc.p, ctx->csr_delta.p, Hp, Hhp, scale, rowmaj ? nchunk : 0);                         \
+        } while (0)
+#define FY_H2_LAUNCH_PM(RW, NW, PM)                                                                                   \
+        do { if (h2_bulk) FY_H2_LAUNCH_B(RW, NW, PM, true); else FY_H2_LAUNCH_B(RW, NW, PM, false); } while (0)
+#define FY_H2_LAUNCH(RW, NW)                                                                                          \
+        do {                                                                                                          \
+            if (!Hhp) FY_H2_LAUNCH_PM(RW, NW, 0);                                                                     \
+            else if (mode == 2) FY_H2_LAUNCH_PM(RW, NW, 2);                                                           \
+            else FY_H2_LAUNCH_PM(RW, NW, 1);                                                                          \
+        } while (0)
+        if (build_variant == 2) {
+            switch (h2_cfg) {
+                case 1: FY_H2_LAUNCH(2048, 2); break;
+                case 2: FY_H2_LAUNCH(512, 8); break;
+                case 3: FY_H2_LAUNCH(1024, 4); break;
+                case 4: FY_H2_LAUNCH(768, 4); break;
+                case 5: FY_H2_LAUNCH(1024, 2); break;
+                default: FY_H2_LAUNCH(1536, 2); break;
+            }
+            return;
+        }
+#undef FY_H2_LAUNCH
+#undef FY_H2_LAUNCH_PM
+#undef FY_H2_LAUNCH_B
+        const size_t smem = (size_t)H_SLICE * H_WARPS * sizeof(double);      // 8 warps x H_SLICE doubles
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_build_H, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH_ON(ctx, strm, k_build_H, dim3(I_c, nchunk), H_THREADS, smem, I_c, ld, n_bound - 1, slot0,
+                  ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, ctx->c_alpha.p, ctx->csc_lu.p, ctx->csc_delta.p,
+                  cp, ctx->csr_loc.p, ctx->csr_delta.p, Hp, Hhp, mode, scale);
     };
     {   // size the per-cluster buffers once (growing them inside the loop would synchronise the device)
         size_t need_h = 0, need_cp = 0, need_sc = 0, need_us = 0;
@@ -739,12 +832,8 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
             const size_t k = seg_begin(SEG_GRAM, sG);
             LAUNCH_ON(ctx, sG, k_chunk_ptr, cdiv((int64_t)K_c * n_bound, 256), 256, 0, cs, K_c, n_bound, slice_w,
                       ctx->rowptr.p, ctx->csr_loc.p, ctx->chunk_ptr2[hb].p);
-            const size_t smem = (size_t)chunk_w * sizeof(double);      // 8 warps x H_SLICE doubles
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_build_H, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LAUNCH_ON(ctx, sG, k_build_H, dim3(I_c, nchunk), H_THREADS, smem, I_c, ld, n_bound - 1, slot0,
-                      ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, ctx->c_alpha.p, ctx->csc_lu.p, ctx->csc_delta.p,
-                      ctx->chunk_ptr2[hb].p, ctx->csr_loc.p, ctx->csr_delta.p, ctx->H[hb].p,
-                      use_hi ? ctx->Hh[hb].p : (uint32_t*)nullptr, plan[c].mode, plan[c].scale);
+            launch_build(sG, I_c, ld, nchunk, n_bound, slot0, ctx->chunk_ptr2[hb].p, ctx->H[hb].p,
+                         use_hi ? ctx->Hh[hb].p : (uint32_t*)nullptr, plan[c].mode, plan[c].scale);
             seg_end(k, sG);
         }
         CK(cudaEventRecord(hReady[hb], sG));

@@ -55,7 +55,8 @@ constexpr int TOPN_MAX_SELECT = 4096;
 __global__ void k_make_keys(const int32_t* __restrict__ r_user, const int32_t* __restrict__ r_item,
                             const float* __restrict__ r_score, int64_t nnz,
                             const int32_t* __restrict__ uid_sorted, const int32_t* __restrict__ uid_rank,
-                            int32_t n_users, int item_bits, int32_t max_item_allowed,
+                            int32_t n_users, const int32_t* __restrict__ uid_table, int32_t uid_table_n, int32_t uid_table_min,
+                            int item_bits, int32_t max_item_allowed,
                             uint64_t* __restrict__ keys, unsigned long long* __restrict__ n_valid,
                             int* __restrict__ flags) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,12 +65,18 @@ __global__ void k_make_keys(const int32_t* __restrict__ r_user, const int32_t* _
         uint64_t key = ~0ull;
         if (r_score[e] > 0.0f) {
             const int32_t uid = r_user[e];
-            int lo = 0, hi = n_users - 1, rank = -1;
-            while (lo <= hi) {
-                const int mid = (lo + hi) >> 1;
-                const int32_t v = uid_sorted[mid];
-                if (v == uid) { rank = uid_rank[mid]; break; }
-                if (v < uid) lo = mid + 1; else hi = mid - 1;
+            int rank = -1;
+            if (uid_table) {                                  // dense ids: one load
+                const int64_t o = (int64_t)uid - (int64_t)uid_table_min;
+                if (o >= 0 && o < uid_table_n) rank = uid_table[o];
+            } else {
+                int lo = 0, hi = n_users - 1;
+                while (lo <= hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const int32_t v = uid_sorted[mid];
+                    if (v == uid) { rank = uid_rank[mid]; break; }
+                    if (v < uid) lo = mid + 1; else hi = mid - 1;
+                }
             }
             const int32_t it = r_item[e];
             if (rank < 0) {
@@ -621,6 +628,210 @@ k_build_H(int32_t I_c, int32_t ld, int32_t n_slices, int32_t slot0,
         for (int32_t i = I_c + lane; i < ld; i += 32) {                              // padding columns
             H[(size_t)j * ld + i] = 1.0;
             if (Hh) Hh[(size_t)j * ld + i] = (plane_mode == 2) ? 0x3f800000u : 0x3ff00000u;
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_build_H2 (round 2): the same H, bit for bit, without the flattened-list search.
+// One warp owns (row j, a range of RW columns) with an fp64 accumulator row in shared memory and walks the
+// raters of j strictly in ascending order, ONE rater at a time, lanes over that rater's entries inside the
+// range (a rater's columns are distinct: no conflict, no match_any, no binary search, no shuffle scan).
+// The first 32 entries of the NEXT rater are gathered into registers before the current rater is
+// accumulated, so one L2 gather is always in flight per warp; ~28 warps per SM hide the rest.
+// Per rater the warp issues ~30 instructions (4 shuffles, 2 gathers, 1 multiply, 1 shared-memory
+// read-add-write) against ~100 per 32 flattened entries in k_build_H; the price is lane use (the
+// work-weighted rater has ~15 entries in a 1024-column range at ML-20M shape, ~60 at Netflix shape).
+// The write-out handles 4 columns per lane per step and is specialised on the plane mode.
+// Summation order per accumulator = ascending rater, separate multiply and add: identical to k_build_H.
+// ---------------------------------------------------------------------------------------------
+template <int RW, int NW, int PM /* 0 = fp64 plane only, 1 = + hi words, 2 = + float(H * plane_scale) */, bool BULK /* write-out by cp.async.bulk */>
+__global__ void __launch_bounds__(NW * 32)
+k_build_H2(int32_t I_c, int32_t ld, int32_t n_ranges, int32_t slot0,
+           const int32_t* __restrict__ c_start, const int32_t* __restrict__ c_len,
+           const double* __restrict__ c_b, const double* __restrict__ c_alpha,
+           const int32_t* __restrict__ csc_lu, const double* __restrict__ csc_delta,
+           const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ csr_loc,
+           const double* __restrict__ csr_delta, double* __restrict__ H, uint32_t* __restrict__ Hh,
+           double plane_scale, int32_t nchunk /* CTAs per row; the grid is linear, row-major: the CTAs in flight write neighbouring memory */) {
+    static_assert(RW % 128 == 0, "the write-out takes 128 columns per warp step");
+    extern __shared__ __align__(16) unsigned char h2_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t j, qb;
+    if (nchunk > 0) { j = (int32_t)(blockIdx.x / (unsigned)nchunk); qb = (int32_t)(blockIdx.x % (unsigned)nchunk); }
+    else { j = blockIdx.x; qb = blockIdx.y; }
+    const int32_t q = qb * NW + warp;
+    if (q >= n_ranges) return;
+    double* __restrict__ acc = reinterpret_cast<double*>(h2_smem) + (size_t)warp * RW;
+    const int32_t c0 = q * RW;
+    const int32_t w = min(RW, I_c - c0);
+    const int32_t nb = n_ranges + 1;
+    const int32_t x0 = c_start[slot0 + j], nr = c_len[slot0 + j];
+
+    // lane r of a group: rater g + r of row j -> its delta and its entry range inside this column range
+    int32_t lo_n = 0, cnt_n = 0;
+    double d_n = 0.0;
+    if (lane < nr) {
+        const int32_t x = x0 + lane;
+        const size_t bp = (size_t)csc_lu[x] * nb + q;
+        d_n = csc_delta[x];
+        lo_n = chunk_ptr[bp];
+        cnt_n = chunk_ptr[bp + 1] - lo_n;
+    }
+#pragma unroll 4
+    for (int t = lane * 2; t < RW; t += 64) *reinterpret_cast<double2*>(acc + t) = make_double2(0.0, 0.0);
+    __syncwarp();
+
+    const double* __restrict__ accb = acc - c0;                          // indexed by the cluster-local column
+    double* __restrict__ accw = acc - c0;
+    for (int32_t g = 0; g < nr; g += 32) {
+        const int32_t lo_l = lo_n, cnt_l = cnt_n;
+        const double d_l = d_n;
+        lo_n = 0; cnt_n = 0; d_n = 0.0;
+        if (g + 32 + lane < nr) {                                        // next group's registers, in flight during this group
+            const int32_t x = x0 + g + 32 + lane;
+            const size_t bp = (size_t)csc_lu[x] * nb + q;
+            d_n = csc_delta[x];
+            lo_n = chunk_ptr[bp];
+            cnt_n = chunk_ptr[bp + 1] - lo_n;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, cnt_l > 0);              // raters with entries here; bit order = ascending rater
+        if (m == 0u) continue;
+        // Raters are taken in batches of PF; the gathers of batch B are issued before batch A is accumulated and
+        // vice versa, so PF..2*PF gathers are in flight per warp (the single-step look-ahead was latency bound:
+        // 25 % of the stall samples sat on the first use of the gathered column).
+        constexpr int PF = 4;
+        int32_t loA[PF], cntA[PF], colA[PF], loB[PF], cntB[PF], colB[PF];
+        double dA[PF], dlA[PF], dB[PF], dlB[PF];
+        auto fetch = [&](int32_t (&lo)[PF], int32_t (&cnt)[PF], int32_t (&col)[PF], double (&d)[PF], double (&dl)[PF]) {
+#pragma unroll
+            for (int z = 0; z < PF; z++) {
+                cnt[z] = 0; lo[z] = 0; col[z] = c0; d[z] = 0.0; dl[z] = 0.0;
+                if (m) {
+                    const int r = __ffs(m) - 1;
+                    m &= m - 1;
+                    lo[z] = __shfl_sync(0xffffffffu, lo_l, r);
+                    cnt[z] = __shfl_sync(0xffffffffu, cnt_l, r);
+                    d[z] = __shfl_sync(0xffffffffu, d_l, r);
+                    if (lane < cnt[z]) { col[z] = csr_loc[lo[z] + lane]; dl[z] = csr_delta[lo[z] + lane]; }
+                }
+            }
+        };
+        auto consume = [&](const int32_t (&lo)[PF], const int32_t (&cnt)[PF], const int32_t (&col)[PF], const double (&d)[PF],
+                           const double (&dl)[PF]) {
+#pragma unroll
+            for (int z = 0; z < PF; z++) {
+                if (cnt[z] > 0) {
+                    if (lane < cnt[z]) accw[col[z]] = __dadd_rn(accb[col[z]], __dmul_rn(d[z], dl[z]));
+                    if (cnt[z] > 32) {                                   // a heavy rater: its further entries, 4 gathers in flight
+                        for (int32_t k = 32 + lane; k < cnt[z]; k += 128) {
+                            int32_t c2[4];
+                            double v2[4];
+#pragma unroll
+                            for (int y = 0; y < 4; y++) {
+                                const bool in = k + 32 * y < cnt[z];
+                                c2[y] = in ? csr_loc[lo[z] + k + 32 * y] : -1;
+                                v2[y] = in ? csr_delta[lo[z] + k + 32 * y] : 0.0;
+                            }
+#pragma unroll
+                            for (int y = 0; y < 4; y++)
+                                if (c2[y] >= 0) accw[c2[y]] = __dadd_rn(accb[c2[y]], __dmul_rn(d[z], v2[y]));
+                        }
+                    }
+                    __syncwarp();                                        // the next rater may hit columns other lanes just updated
+                }
+            }
+        };
+        fetch(loA, cntA, colA, dA, dlA);
+        for (;;) {
+            fetch(loB, cntB, colB, dB, dlB);
+            consume(loA, cntA, colA, dA, dlA);
+            if (cntB[0] == 0) break;
+            fetch(loA, cntA, colA, dA, dlA);
+            consume(loB, cntB, colB, dB, dlB);
+            if (cntA[0] == 0) break;
+        }
+    }
+    __syncwarp();
+    // write-out: H = acc + b_j * alpha (one fma, as k_build_H), 4 columns per lane per step
+    const double bj = c_b[slot0 + j];
+    double* __restrict__ row = H + (size_t)j * ld + c0;
+    const double* __restrict__ al = c_alpha + slot0 + c0;
+    uint32_t* __restrict__ rowh = (PM != 0) ? Hh + (size_t)j * ld + c0 : nullptr;
+    if (BULK) {
+        // The row segment is finished in place in shared memory and leaves through the bulk-copy engine: 8.4 GB of
+        // 16-byte LSU stores per cluster queued in the same L1 FIFO as every gather of the SM (ncu: the loads of the
+        // write-out and of the accumulate phase waited thousands of cycles behind them).
+        const int32_t wp = min(RW, ld - c0);                             // padding columns of the last range included
+#pragma unroll 4
+        for (int t = lane * 2; t < wp; t += 64) {
+            double2 a = *reinterpret_cast<const double2*>(acc + t);
+            a.x = (t < w) ? __fma_rn(bj, __ldg(al + t), a.x) : 1.0;
+            a.y = (t + 1 < w) ? __fma_rn(bj, __ldg(al + t + 1), a.y) : 1.0;
+            *reinterpret_cast<double2*>(acc + t) = a;
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                         :: "l"(row), "r"((unsigned)__cvta_generic_to_shared(acc)), "r"((unsigned)wp * 8u) : "memory");
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
+        if (PM != 0) {
+            // 4-byte plane: converted in place, front to back (step s reads bytes [512 s, 512 s + 512) and writes
+            // [256 s, 256 s + 256), which every earlier step has already consumed), after the fp64 copy has read the row
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+            __syncwarp();
+            uint32_t* __restrict__ accf = reinterpret_cast<uint32_t*>(acc);
+            for (int t = lane * 2; t < wp; t += 64) {
+                const double2 a = *reinterpret_cast<const double2*>(acc + t);
+                __syncwarp();
+                uint2 o = (PM == 2)
+                    ? make_uint2(__float_as_uint((float)(a.x * plane_scale)), __float_as_uint((float)(a.y * plane_scale)))
+                    : make_uint2(hi_word_rn(a.x), hi_word_rn(a.y));
+                if (PM == 2 && t >= w) o = make_uint2(0x3f800000u, 0x3f800000u);     // padding columns: 1.0f, as k_build_H
+                *reinterpret_cast<uint2*>(accf + t) = o;
+            }
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                             :: "l"(rowh), "r"((unsigned)__cvta_generic_to_shared(acc)), "r"((unsigned)wp * 4u) : "memory");
+                asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // shared memory is released at exit
+        __syncwarp();
+        return;
+    }
+    const int32_t w4 = w & ~3;
+#pragma unroll 4
+    for (int t = lane * 4; t < w4; t += 128) {
+        const double a0 = __ldg(al + t), a1 = __ldg(al + t + 1), a2 = __ldg(al + t + 2), a3 = __ldg(al + t + 3);
+        const double2 s0 = *reinterpret_cast<const double2*>(acc + t);
+        const double2 s1 = *reinterpret_cast<const double2*>(acc + t + 2);
+        double2 o0, o1;
+        o0.x = __fma_rn(bj, a0, s0.x); o0.y = __fma_rn(bj, a1, s0.y);
+        o1.x = __fma_rn(bj, a2, s1.x); o1.y = __fma_rn(bj, a3, s1.y);
+        *reinterpret_cast<double2*>(row + t) = o0;
+        *reinterpret_cast<double2*>(row + t + 2) = o1;
+        if (PM == 2)
+            *reinterpret_cast<uint4*>(rowh + t) = make_uint4(__float_as_uint((float)(o0.x * plane_scale)), __float_as_uint((float)(o0.y * plane_scale)),
+                                                              __float_as_uint((float)(o1.x * plane_scale)), __float_as_uint((float)(o1.y * plane_scale)));
+        else if (PM == 1)
+            *reinterpret_cast<uint4*>(rowh + t) = make_uint4(hi_word_rn(o0.x), hi_word_rn(o0.y), hi_word_rn(o1.x), hi_word_rn(o1.y));
+    }
+    if (lane < w - w4) {                                                 // last 1..3 columns of the last range
+        const int t = w4 + lane;
+        const double o = __fma_rn(bj, al[t], acc[t]);
+        row[t] = o;
+        if (PM == 2) rowh[t] = __float_as_uint((float)(o * plane_scale));
+        else if (PM == 1) rowh[t] = hi_word_rn(o);
+    }
+    if (q == n_ranges - 1)
+        for (int32_t i = I_c + lane; i < ld; i += 32) {                              // padding columns
+            H[(size_t)j * ld + i] = 1.0;
+            if (PM == 2) Hh[(size_t)j * ld + i] = 0x3f800000u;
+            else if (PM == 1) Hh[(size_t)j * ld + i] = 0x3ff00000u;
         }
 }
 

@@ -302,10 +302,18 @@ int orc_rm2_run(const orc_params* p,
 #pragma omp parallel for schedule(dynamic, 4)
             for (int64_t i = 0; i < I; i++)
                 for (int64_t j = i; j < I; j++) {
+                    /* four partial sums (v mod 4), combined at the end: GRAM is the algebra cross-check,
+                     * its order is not the reducer's (LITERAL* keep the reducer's order) */
                     const double* a = P + (size_t)i * (size_t)K;
                     const double* b = P + (size_t)j * (size_t)K;
-                    double s = 0;
-                    for (int64_t v = 0; v < K; v++) s += a[v] * b[v];
+                    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                    int64_t v = 0;
+                    for (; v + 4 <= K; v += 4) {
+                        s0 += a[v] * b[v]; s1 += a[v + 1] * b[v + 1];
+                        s2 += a[v + 2] * b[v + 2]; s3 += a[v + 3] * b[v + 3];
+                    }
+                    for (; v < K; v++) s0 += a[v] * b[v];
+                    const double s = (s0 + s1) + (s2 + s3);
                     G[(size_t)i * (size_t)I + (size_t)j] = s;
                     G[(size_t)j * (size_t)I + (size_t)i] = s;
                 }
@@ -327,7 +335,13 @@ int orc_rm2_run(const orc_params* p,
         const double log_K = log((double)K);              /* :329 */
         const double t_begin = now_s();
         int oom = 0;
-#pragma omp parallel for schedule(dynamic, 1)
+        int64_t n_slots_used = 0;
+        for (int64_t v = 0; v < K; v++) n_slots_used += (slot[v] >= 0);
+        /* Users are independent (one reduce task scores them one after the other); with fewer wanted users
+         * than threads the candidates of a user are spread over the threads instead, so that every host
+         * core is busy.  The arithmetic per (user, candidate) is the same either way. */
+        const int inner_par = (n_slots_used < (int64_t)threads);
+#pragma omp parallel for schedule(dynamic, 1) if (!inner_par)
         for (int64_t u = 0; u < K; u++) {
             if (slot[u] < 0) continue;
             const int64_t r0 = rowptr[u0 + u], r1 = rowptr[u0 + u + 1];
@@ -336,12 +350,15 @@ int orc_rm2_run(const orc_params* p,
             cand_t* prefs = (cand_t*)malloc(sizeof(cand_t) * (size_t)cu);
             char* rated = (char*)calloc((size_t)I, 1);
             int32_t* rj = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
-            if (!prefs || !rated || !rj) { oom = 1; free(prefs); free(rated); free(rj); continue; }
+            int32_t* cand_i = (int32_t*)malloc(sizeof(int32_t) * (size_t)(cu > 0 ? cu : 1));
+            if (!prefs || !rated || !rj || !cand_i) { oom = 1; free(prefs); free(rated); free(rj); free(cand_i); continue; }
             for (int k = 0; k < n; k++) { rj[k] = loc[rt[r0 + k].item]; rated[rj[k]] = 1; }
             const double pvpi = (n - 1) * log_items - n * log_K;               /* :328-329 */
             int64_t np = 0;
-            for (int64_t i = 0; i < I; i++) {                                   /* :332 */
-                if (rated[i]) continue;
+            for (int64_t i = 0; i < I; i++) if (!rated[i]) cand_i[np++] = (int32_t)i;   /* unratedItems :206-208 */
+#pragma omp parallel for schedule(dynamic, 8) if (inner_par)
+            for (int64_t q = 0; q < np; q++) {                                  /* :332 */
+                const int64_t i = cand_i[q];
                 double logResult = 0.0;                                        /* :334 */
                 for (int k = 0; k < n; k++) {                                   /* :337 */
                     const int64_t j = rj[k];
@@ -362,9 +379,8 @@ int orc_rm2_run(const orc_params* p,
                     logResult += log(sum);                                     /* :348 */
                 }
                 logResult += pvpi;                                             /* :352 */
-                prefs[np].score = logResult;
-                prefs[np].item = items[i];
-                np++;
+                prefs[q].score = logResult;
+                prefs[q].item = items[i];
             }
             qsort(prefs, (size_t)np, sizeof(cand_t), cmp_cand);
             const int64_t iterations = np < p->top_n ? np : p->top_n;          /* :360 */
@@ -374,7 +390,7 @@ int orc_rm2_run(const orc_params* p,
                 res->score[slot[u] + k] = prefs[k].score;
                 res->cluster[slot[u] + k] = c;
             }
-            free(prefs); free(rated); free(rj);
+            free(prefs); free(rated); free(rj); free(cand_i);
         }
         res->seconds += now_s() - t_begin;
         for (int64_t v = 0; v < K; v++) if (slot[v] >= 0) res->users_scored++;
