@@ -122,46 +122,70 @@ def workload_figures(r):
 _CPU_CAL = {}
 
 
-def cpu_baseline(r, budget_s=8.0, seed=12345):
-    """The oracle ("port" of M/rm/AbstractRM2Reducer.java:129-233,321-371) on a bounded, seeded sample of users
-    of one cluster, all host threads; users/s extrapolated by inner-loop work to the workload's mean user."""
+def _stratified_sample(r, n_u, n_users, n_clusters, seed):
+    """>= n_users users over n_clusters (seeded) clusters, each cluster's users taken at evenly spaced quantiles of
+    the rated-item count n_u ("seeded, size-stratified sample of >= 256 users")."""
+    rng = np.random.default_rng(seed)
+    clusters = rng.choice(r.n_clusters, size=min(n_clusters, r.n_clusters), replace=False)
+    per = -(-n_users // len(clusters))
+    out = []
+    for c in clusters:
+        members = r.cl_user[r.cl_cluster == c]
+        members = members[np.argsort(n_u[members], kind="stable")]
+        k = min(per, len(members))
+        pos = ((np.arange(k) + rng.random()) * len(members) / k).astype(np.int64).clip(0, len(members) - 1)
+        out.append(members[np.unique(pos)])
+    return np.concatenate(out).astype(np.int32), [int(c) for c in clusters]
+
+
+def cpu_baseline(r, budget_s=20.0, seed=12345, n_sample=256):
+    """The oracle ("port" of M/rm/AbstractRM2Reducer.java:129-233,321-371) on a bounded, seeded, size-stratified sample:
+    >= 256 users over 4 clusters, every host thread busy ((user, 64-candidate block) tasks).  The literal loop nest costs
+    2*K*n_u flops per (user, candidate) whatever the candidate, so each sampled user scores every s-th candidate and the
+    time is multiplied by s (s chosen from a calibration run to fit the budget); users/s = users of the sample / (wall * s),
+    cross-checked by the work-normalised figure.  Also reports the single-thread MODE_LITERAL rate (what one reduce task of
+    Hadoop local mode executes)."""
     from oracle import rm2_oracle as orc
     cores = os.cpu_count() or 1
     terms_total, i_c, n_u = workload_figures(r)
     ksz = r.cluster_size.astype(np.float64)
-    mean_inner = float(np.mean(ksz[r.cl_cluster] * n_u[r.cl_user] * i_c[r.cl_cluster]))
-    # sample users of one (seeded) cluster so that one P cache is built, like one reduce() call
-    rng = np.random.default_rng(seed)
-    c = int(rng.integers(0, r.n_clusters))
-    members = rng.permutation(r.cl_user[r.cl_cluster == c])
-    inner = lambda us: float(np.sum(ksz[c] * n_u[us] * i_c[c]))
+    inner_of = lambda us: ksz[cl_of[us]] * n_u[us] * i_c[cl_of[us]]
+    cl_of = np.zeros(r.n_users + 1, np.int64)
+    cl_of[r.cl_user] = r.cl_cluster
+    mean_inner = float(np.mean(inner_of(r.cl_user)))
+    sample, clusters = _stratified_sample(r, n_u, n_sample, 4, seed)
+    run = lambda us, stride, mode, threads: orc.run(r.user, r.item, r.score, r.cl_user, r.cl_cluster, r.cluster_size, LAMBDA,
+                                                    r.n_items, TOP_N, mode=mode, threads=threads, only_users=us, cand_stride=stride)
     t0 = time.time()
     if "rate" not in _CPU_CAL:
-        # calibrate once on the lightest users (they run ~3x faster per unit of work than the average user)
-        light = members[np.argsort(n_u[members])[:max(2, min(cores, len(members)))]]
-        cal = orc.run(r.user, r.item, r.score, r.cl_user, r.cl_cluster, r.cluster_size, LAMBDA, r.n_items, TOP_N,
-                      mode=orc.MODE_LITERAL_FAST, threads=cores, only_users=light)
-        _CPU_CAL["rate"] = inner(light) / max(cal["seconds"], 1e-3) / 3.0   # inner iterations / s with all cores
-    target = _CPU_CAL["rate"] * budget_s
-    sample, acc = [], 0.0
-    for u in members:
-        sample.append(int(u)); acc += float(ksz[c] * n_u[u] * i_c[c])
-        if acc >= target and len(sample) >= min(cores, 8):
-            break
+        # calibration: the sample of ONE cluster at a coarse stride (all threads) and 4 light users (one thread, MODE_LITERAL)
+        one = sample[cl_of[sample] == clusters[0]]
+        s_cal = max(1, int(np.ceil(float(np.sum(inner_of(one))) / (2.0e9 * cores))))      # ~1 s at 2e9 inner iterations/s/core
+        cal = run(one, s_cal, orc.MODE_LITERAL_FAST, cores)
+        _CPU_CAL["rate"] = float(np.sum(inner_of(one))) / s_cal / max(cal["seconds"], 1e-3)
+        light = one[:4]
+        s1 = max(1, int(np.ceil(float(np.sum(inner_of(light))) / 2.0e9)))
+        lit = run(light, s1, orc.MODE_LITERAL, 1)
+        _CPU_CAL["literal_1thread_users_per_s"] = (float(np.sum(inner_of(light))) / s1 / max(lit["seconds"], 1e-3)) / mean_inner
+        _CPU_CAL["literal_1thread_sample"] = "%d light users, every %d-th candidate, %.1f s" % (len(light), s1, lit["seconds"])
+    work = float(np.sum(inner_of(sample)))
+    stride = max(1, int(np.ceil(work / (_CPU_CAL["rate"] * budget_s))))
     cal_s = time.time() - t0
-    out = orc.run(r.user, r.item, r.score, r.cl_user, r.cl_cluster, r.cluster_size, LAMBDA, r.n_items, TOP_N,
-                  mode=orc.MODE_LITERAL_FAST, threads=cores, only_users=np.array(sample, np.int32))
+    out = run(sample, stride, orc.MODE_LITERAL_FAST, cores)
     secs = max(out["seconds"], 1e-6)
-    users_per_s_sample = len(sample) / secs
-    # extrapolate by work: the sample's inner-iteration rate applied to the workload's mean user
-    users_per_s = (inner(np.array(sample)) / secs) / mean_inner
-    return {"value": users_per_s, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d users of cluster %d (K=%d, I_c=%d), scoring loops only (%.1f s wall, %d threads, "
-                      "oracle MODE_LITERAL_FAST = the Java loop nest's arithmetic and order on a transposed P cache); "
-                      "users/s extrapolated by inner-loop work K*n_u*I_c to the workload's mean user "
-                      "(sample itself: %.3f users/s); Hadoop/JVM overheads not modelled"
-                      % (len(sample), c, int(ksz[c]), int(i_c[c]), secs, cores, users_per_s_sample),
-            "calibration_s": cal_s}
+    direct = len(sample) / (secs * stride)
+    by_work = (work / stride / secs) / mean_inner
+    return {"value": by_work, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d users at evenly spaced n_u quantiles of clusters %s (n_u %d..%d, mean %.0f; workload mean %.0f), every %d-th "
+                      "candidate of each user, scoring loops only: %.1f s wall on %d threads ((user, 64-candidate) tasks, all busy); "
+                      "oracle MODE_LITERAL_FAST = the Java loop nest's arithmetic and order on a transposed P cache; users/s = "
+                      "work-normalised (inner iterations K*n_u*I_c per second / the workload's mean per user); the sample's own "
+                      "users/(wall*stride) = %.3f; Hadoop/JVM overheads not modelled"
+                      % (len(sample), clusters, int(n_u[sample].min()), int(n_u[sample].max()), float(n_u[sample].mean()),
+                         float(n_u[r.cl_user].mean()), stride, secs, out["threads"], direct),
+            "users_per_s_sample_direct": direct, "cand_stride": stride, "sample_users": int(len(sample)),
+            "literal_1thread_users_per_s": _CPU_CAL["literal_1thread_users_per_s"],
+            "literal_1thread_sample": _CPU_CAL["literal_1thread_sample"], "calibration_s": cal_s}
 
 
 def run_reference_arm(args, r, workload):
@@ -170,7 +194,7 @@ def run_reference_arm(args, r, workload):
     if rank != 0:
         return
     vals, last = [], None
-    budget = max(2.0, min(8.0, 60.0 / max(1, args.steps + args.warmup)))
+    budget = max(4.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
     for s in range(args.warmup + args.steps):
         last = cpu_baseline(r, budget_s=budget, seed=12345 + s)
         if s >= args.warmup:
@@ -182,7 +206,8 @@ def run_reference_arm(args, r, workload):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload, "cpu_baseline": last,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "CPU restatement of the reference (no JVM in this image); ms_per_step = extrapolated whole job"}
+            "note": "CPU restatement of the reference (no JVM in this image); each step = a fresh seeded stratified sample; "
+                    "ms_per_step = extrapolated whole job"}
     emit(json.dumps(line))
 
 
@@ -210,6 +235,53 @@ def emit(line):
         os.write(_REAL_STDOUT, (line + "\n").encode())
 
 
+def secondary_benchmarks(r, local_rank):
+    """Config 3 (item-item co-occurrence, int8 tcgen05 GEMM) at ML-1M and at this workload's shape, and the PPC
+    clustering step (f2) at this workload's shape, each with its own clock sample (N = 1 only, after the main run)."""
+    import filmyou_core_b200 as fy
+    from filmyou_core_b200 import datagen
+    out = {}
+
+    def timed(fn):
+        smp = ClockSampler(local_rank); smp.start()
+        v = fn()
+        v["clocks"] = smp.stop()
+        return v
+
+    def cooc(rr, reps=5):
+        def go():
+            with fy.Rm2Engine(lam=LAMBDA, number_of_items=rr.n_items, top_n=TOP_N, device=local_rank) as e:
+                e.set_ratings(rr.user, rr.item, rr.score)
+                ms = [e.cooc_counts(rr.n_users + 1, rr.n_items + 1, want_counts=False)[1] for _ in range(reps + 1)][1:]
+            best = float(np.min(ms))
+            n, k = rr.n_items + 1, rr.n_users + 1
+            return {"ms_gemm": best, "ms_all": ms, "algorithmic_int8_pop_per_s": 2.0 * n * n * k / (best * 1e-3) / 1e15,
+                    "shape": "%d x %d items over %d users" % (n, n, k)}
+        return timed(go)
+    try:
+        out["cooc_ml1m"] = cooc(datagen.generate("ml-1m"))
+        out["cooc_workload_shape"] = cooc(r, reps=3)
+    except Exception as ex:            # reported, never fatal for the headline line
+        out["cooc_error"] = repr(ex)
+    try:
+        from filmyou_core_b200.nmf import PPC, NmfEngine
+        def ppc():
+            ids, inv = np.unique(r.item, return_inverse=True)          # the PPC jobs need every item id rated (WComputationMapper.java:95-98)
+            with NmfEngine(PPC, r.n_users, len(ids), r.n_clusters, 10, device=local_rank) as e:
+                e.set_ratings(r.user, (inv + 1).astype(np.int32), r.score)
+                best = None
+                for rep in range(3):
+                    e.init_random(rep)
+                    e.run()
+                    p = e.profile()
+                    best = p if best is None or p["ms_per_iteration"] < best["ms_per_iteration"] else best
+            return {"ms_per_iteration": best["ms_per_iteration"], "ms_index": best["ms_index"], "k": r.n_clusters, "iterations": 10}
+        out["ppc_workload_shape"] = timed(ppc)
+    except Exception as ex:
+        out["ppc_error"] = repr(ex)
+    return out
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -220,6 +292,7 @@ def main():
     ap.add_argument("--workload", default="ml-20m")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--score-mode", type=int, default=0, help="0 = hi-word stream + exact re-score (default), 1 = fp64 stream")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -240,10 +313,10 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args, r, workload)
 
+    import hashlib
     import torch
     import torch.distributed as dist
     import filmyou_core_b200 as fy
-    from filmyou_core_b200 import sharding
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -260,20 +333,20 @@ def main():
                        shard_rank=rank, shard_count=world, score_mode=args.score_mode)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)          # torch.cuda.Event then times the launching stream
-
-    def gather():
-        if world == 1:
-            return None
-        d = eng.results_device()
-        local = {k: torch.as_tensor(v, device=dev) for k, v in d.items()} if eng.result_count() else \
-                {k: torch.empty(0, device=dev) for k in d}
-        return sharding.gather_results(local, device=dev)
+    if world > 1:
+        # the exchange step lives inside libfilmyou_rm2.so: rank 0's ncclUniqueId reaches the other ranks through torch
+        # (plumbing), every rank attaches its own communicator, and fy_rm2_run ends with one grouped NCCL exchange
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(fy.Rm2Engine.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        eng.comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank)
 
     # ---- device-resident: ratings already in HBM ----
     eng.set_ratings(r.user, r.item, r.score)
     eng.set_clustering(r.cl_user, r.cl_cluster, r.cluster_size)
     for _ in range(args.warmup):
-        eng.run(); gather()
+        eng.run()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -283,7 +356,7 @@ def main():
     barrier()
     ev0.record(stream)
     for _ in range(args.steps):
-        eng.run(); gather()
+        eng.run()
         p = eng.profile(); profs.append(p); launches += p["kernel_launches"]
     ev1.record(stream)
     barrier()
@@ -295,7 +368,8 @@ def main():
                          sum(p["ms_topn"] for p in profs), float(launches),
                          float(sum(p["score_launches"] for p in profs)), sum(p["ms_refine"] for p in profs),
                          float(profs[-1]["bytes_per_term"]), float(sum(p["exact_rerun"] for p in profs)),
-                         float(profs[-1]["score_kernel"])],
+                         float(profs[-1]["score_kernel"]), sum(p["ms_gather"] for p in profs),
+                         sum(p["gram_bytes"] for p in profs), float(sum(p["clusters_touched"] for p in profs))],
                         dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -308,45 +382,87 @@ def main():
     users = float(scored.item())
     value = users / (ms_per_step * 1e-3)
 
-    # ---- end to end: host buffers in, host triples out, every step ----
+    # ---- digest of the job's output: with the communicator attached every rank holds ALL triples, so the digest of
+    # rank 0 at N = 2/4/8 must equal the N = 1 digest (ids and fp64 score bits) ----
+    digest = None
+    if rank == 0:
+        res = eng.results()
+        h = hashlib.sha256()
+        for k in ("user", "item", "score64"):
+            h.update(np.ascontiguousarray(res[k]).tobytes())
+        digest = {"result_sha256": h.hexdigest(), "triples": int(len(res["user"])),
+                  "over": "(user, item, score64 bits) of every emitted triple in (cluster, user id, rank) order, read on rank 0 "
+                          "after the in-library exchange"}
+        del res
+
+    # ---- end to end: host buffers in, host triples out, every step.  The job's output lands in ONE host buffer shared by
+    # the ranks of the node (each rank copies its shard's (item, score64) stream into its slice, like one part file per
+    # reduce task, M/rm/RM2Job.java:244-251) plus one (user, cluster, count) record per row; no device-side exchange. ----
     e2e = None
     if not args.no_e2e:
+        if world > 1:
+            eng.comm_destroy()
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         h_user, h_item, h_score = pin(r.user), pin(r.item), pin(r.score)
         n_max = r.n_users * TOP_N
-        outp = dict(user=torch.empty(n_max, dtype=torch.int32).pin_memory(), item=torch.empty(n_max, dtype=torch.int32).pin_memory(),
-                    score64=torch.empty(n_max, dtype=torch.float64).pin_memory(), score32=torch.empty(n_max, dtype=torch.float32).pin_memory(),
-                    cluster=torch.empty(n_max, dtype=torch.int32).pin_memory())
-        outn = {k: v.numpy() for k, v in outp.items()}
+        shm = "/dev/shm/fy_bench_%s_%d.bin" % (os.environ.get("MASTER_PORT", "0"), os.getuid())
+        if rank == 0:
+            with open(shm, "wb") as f:
+                f.truncate(n_max * 12)
+        barrier()
+        host = np.memmap(shm, dtype=np.uint8, mode="r+", shape=(n_max * 12,))
+        rt = torch.cuda.cudart()
+        assert int(rt.cudaHostRegister(host.ctypes.data, host.nbytes, 0)) == 0, "cudaHostRegister failed"
+        out_item = host[:n_max * 4].view(np.int32)
+        out_s64 = host[n_max * 4:].view(np.float64)
+        bounds = eng.shard_bounds()
+        t_off = int(bounds[rank]) * TOP_N          # dense upper bound: shard r starts at bounds[r] * N triples
 
         def e2e_step():
             eng.set_ratings(h_user.numpy(), h_item.numpy(), h_score.numpy())
             eng.set_clustering(r.cl_user, r.cl_cluster, r.cluster_size)
             eng.run()
-            g = gather()
-            if world == 1:
-                res = eng.results(out=outn)
-                return len(res["user"])
-            n = g["user"].numel()               # every rank reads the gathered triples back to the host
-            for k in outp:
-                outp[k][:n].copy_(g[k], non_blocking=True)
-            torch.cuda.synchronize()
-            return n
+            res = eng.results_compact(out=dict(item=out_item[t_off:], score64=out_s64[t_off:]))
+            return len(res["item"]), len(res["row_user"])
         e2e_step()
         barrier()
         t0 = time.perf_counter()
-        n_out = 0
+        n_out, n_rows = 0, 0
         for _ in range(args.steps):
-            n_out = e2e_step()
+            n_out, n_rows = e2e_step()
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        cnt = torch.tensor([float(n_out), float(n_rows)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         e2e_s = float(dt.item()) / args.steps
+        rt.cudaHostUnregister(host.ctypes.data)
+        del out_item, out_s64, host
+        barrier()
+        if rank == 0:
+            os.unlink(shm)
+        h2d_rank = int(r.nnz * 12 + r.n_users * 8 + r.n_clusters * 4)
         e2e = {"value": users / e2e_s, "unit": UNIT,
-               "h2d_bytes_per_step": int(r.nnz * 12 + r.n_users * 8 + r.n_clusters * 4),
-               "d2h_bytes_per_step": int(n_out * 24), "ms_per_step": e2e_s * 1e3,
-               "timing": "host wall clock around set_ratings+set_clustering+run+results, max over ranks"}
+               "h2d_bytes_per_step": h2d_rank * world,
+               "d2h_bytes_per_step": int(cnt[0].item() * 12 + cnt[1].item() * 12), "ms_per_step": e2e_s * 1e3,
+               "h2d_bytes_per_step_per_rank": h2d_rank,
+               "timing": "host wall clock around set_ratings+set_clustering+run+results (pinned inputs; the (item, score64) stream "
+                         "and the per-row (user, cluster, count) records copied into one host buffer shared by the ranks), max over ranks"}
+
+    # ---- roofline probe: what the L2 -> SM path delivers for the score kernel's access pattern (rank 0, after the timed region) ----
+    probe = None
+    if rank == 0:
+        try:
+            terms_total, i_c, n_u = workload_figures(r)
+            I = int(np.max(i_c)); K = int(np.max(r.cluster_size))
+            rows = int(round(float(np.mean(n_u[r.cl_user]))))
+            smp = ClockSampler(local_rank); smp.start()
+            g, pms = eng.probe_plane_read(I, K, rows, reps=5)
+            probe = {"gb_per_s": g, "ms_per_launch": pms, "plane_rows": I, "users": K, "rows_per_user": rows, "clocks": smp.stop(),
+                     "what": "k_probe_plane_read: k_score_f32's grid and 16-byte loads over an [I_c x ld] 4-byte plane, arithmetic removed"}
+        except Exception as ex:
+            probe = {"error": repr(ex)}
 
     if rank != 0:
         if world > 1:
@@ -360,45 +476,55 @@ def main():
         s = s.tolist()
         per_rank.append({"ms_score": s[0], "score_bytes": s[1], "ms_gram": s[2], "ms_index": s[3], "ms_topn": s[4],
                          "launches": s[5], "score_launches": s[6], "ms_refine": s[7], "bytes_per_term": s[8],
-                         "exact_rerun": s[9], "score_kernel": int(s[10])})
+                         "exact_rerun": s[9], "score_kernel": int(s[10]), "ms_gather": s[11], "gram_bytes": s[12],
+                         "clusters_touched": s[13]})
     worst = max(per_rank, key=lambda x: x["ms_score"])
     achieved = worst["score_bytes"] / (worst["ms_score"] * 1e-3) / 1e9 if worst["ms_score"] > 0 else 0.0
     hi = worst["bytes_per_term"] == 4.0
     kname = ("k_score", "k_score_hi", "k_score_f32")[worst["score_kernel"]]
-    roofline = {"kernel": "fy::" + kname, "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(kname),
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": worst["score_bytes"] / max(worst["score_launches"], 1),
-                "avg_launch_ms": worst["ms_score"] / max(worst["score_launches"], 1),
-                "definition": "%d B per (user, candidate, rated item) log-term = one %s element of H streamed; "
-                              "sum over launches / sum of launch durations (CUDA events on the launching stream); "
-                              "frac > 1 = rows re-used out of L2 (traffic = DRAM bytes per launch from the ncu capture "
-                              "of one ML-20M-sized cluster, profiles/)" % (4 if hi else 8, "hi-word (4-byte)" if hi else "fp64"),
-                "stage_ms_per_step": {k: worst[k] / args.steps for k in ("ms_index", "ms_gram", "ms_score", "ms_topn", "ms_refine")},
+    traffic = ncu_traffic(kname)
+    alg_per_launch = worst["score_bytes"] / max(worst["score_launches"], 1)
+    avg_launch_ms = worst["ms_score"] / max(worst["score_launches"], 1)
+    # Which roof binds: the plane rows are served out of L2 (ncu DRAM traffic is ~5x below the algorithmic bytes), so the
+    # kernel is bounded by the L2 -> SM path, whose ceiling for THIS access pattern is measured on THIS box by the probe.
+    l2_peak = probe.get("gb_per_s") if probe and "gb_per_s" in probe else None
+    roofline = {"kernel": "fy::" + kname, "bound": "l2" if l2_peak else "hbm", "achieved": achieved,
+                "peak": l2_peak if l2_peak else peak, "unit": "GB/s", "frac": achieved / (l2_peak if l2_peak else peak),
+                "traffic": traffic,
+                "peak_source": ("measured live: fy_rm2_probe_plane_read (k_score_f32's loads without its arithmetic), rank 0, "
+                                "after the timed region" if l2_peak else peak_src),
+                "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_launch_ms,
+                "definition": "%d B per (user, candidate, rated item) log-term = one %s element of H streamed; sum over launches / "
+                              "sum of launch durations (CUDA events on the launching stream)" % (4 if hi else 8, "4-byte" if hi else "fp64"),
+                "hbm": {"peak": peak, "peak_source": peak_src, "algorithmic_frac": achieved / peak,
+                        "dram_frac": (traffic / (avg_launch_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                        "note": "algorithmic_frac > 1: rows are re-used out of L2; dram_frac = ncu DRAM bytes per launch (one "
+                                "ML-20M-sized cluster, profiles/) / the live launch time / the measured HBM peak"},
+                "probe": probe,
+                "stage_ms_per_step": {k: worst[k] / args.steps for k in ("ms_index", "ms_gram", "ms_score", "ms_topn", "ms_refine", "ms_gather")},
                 "stages_overlap": "H build, score and top-N/refine run on three streams; stage times are per stream and overlap",
                 "exact_reruns": worst["exact_rerun"]}
-    # The plane rows are served out of L2 (traffic << algorithmic bytes), so the unit that actually bounds this kernel is
-    # the L2 -> SM path: /opt/skills/guides/B300_MICROARCH.md measures a full-chip LTS throughput cap of ~6300 B/clk
-    # (same L2 on B200); at the SM clock sampled during the timed region that is the ceiling reported here.
-    if clocks and clocks.get("sm_mhz"):
-        cap = 6300.0 * clocks["sm_mhz"] * 1e6 / 1e9
-        roofline["l2"] = {"cap_bytes_per_clk": 6300, "sm_mhz": clocks["sm_mhz"], "cap": cap, "unit": "GB/s", "frac": achieved / cap,
-                          "source": "B300_MICROARCH.md 'LTS throughput cap ~6300 B/cyc full-chip'; achieved = the same algorithmic bytes / launch time"}
-    # second kernel of the step, for the record: k_build_H writes the fp64 plane (+ the 4-byte plane in auto mode)
-    gram_bytes = sum(p["gram_bytes"] for p in profs) * (1.5 if hi else 1.0)
-    gram_ms = sum(p["ms_gram"] for p in profs)
-    roofline["secondary"] = {"kernel": "fy::k_build_H", "bound": "hbm", "unit": "GB/s",
-                             "achieved": gram_bytes / (gram_ms * 1e-3) / 1e9 if gram_ms > 0 else 0.0, "peak": peak,
-                             "frac": (gram_bytes / (gram_ms * 1e-3) / 1e9 / peak) if gram_ms > 0 else 0.0,
-                             "definition": "bytes of H written (12 B per element with the 4-byte plane, 8 B without) / time of "
-                                           "the H-build stream segments of rank 0 (CUDA events; the stage overlaps the score kernel)"}
+    # second kernel of the step: the H build writes the fp64 plane (+ the 4-byte plane in auto mode)
+    wg = max(per_rank, key=lambda x: x["ms_gram"])
+    gram_bytes = wg["gram_bytes"] * (1.5 if hi else 1.0)
+    roofline["secondary"] = {"kernel": "fy::k_build_H2", "bound": "hbm", "unit": "GB/s",
+                             "achieved": gram_bytes / (wg["ms_gram"] * 1e-3) / 1e9 if wg["ms_gram"] > 0 else 0.0, "peak": peak,
+                             "frac": (gram_bytes / (wg["ms_gram"] * 1e-3) / 1e9 / peak) if wg["ms_gram"] > 0 else 0.0,
+                             "ms_per_cluster": wg["ms_gram"] / max(wg["clusters_touched"], 1),
+                             "definition": "bytes of H written (12 B per element with the 4-byte plane, 8 B without) / time of the "
+                                           "H-build stream segments of the slowest rank (CUDA events; the stage overlaps the score kernel)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload, "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(sum(p["launches"] for p in per_rank)), "roofline": roofline,
-            "users_scored": users, "datagen_s": t_gen}
+            "users_scored": users, "datagen_s": t_gen, "result_digest": digest,
+            "exchange": ("in-library NCCL exchange of the dense top-N blocks (fy_rm2_comm_init), inside the timed region: %.3f ms per step "
+                         "on the slowest rank" % (max(p["ms_gather"] for p in per_rank) / args.steps)) if world > 1 else None}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(r)
+    if world == 1 and not args.no_secondary:
+        eng.close()
+        line["secondary_benchmarks"] = secondary_benchmarks(r, local_rank)
     emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

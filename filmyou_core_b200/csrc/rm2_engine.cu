@@ -15,6 +15,9 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_segmented_sort.cuh>
 
+#include <dlfcn.h>
+#include <nccl.h>          // types and prototypes only: libnccl.so.2 is resolved with dlopen at run time
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -23,6 +26,7 @@
 #include <cstring>
 #include <new>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -87,7 +91,9 @@ struct fy_rm2_ctx {
     DBuf<int32_t> src_a, csc_src, rowptr;
     DBuf<unsigned char> cub_tmp;
     DBuf<double> usum, isum, iprob, bvec, total, work, work_scan, tsum;
-    DBuf<int32_t> n_u;
+    DBuf<int32_t> n_u, shard_dev;            // shard_dev: bounds[world + 1], rl, rh (k_shard_bounds)
+    std::vector<int32_t> h_bounds;           // shard boundaries of every rank (user ranks)
+    DBuf<double> run_terms;
     DBuf<float> c_score;
     DBuf<unsigned long long> ustat[2];
     bool exact_scores = false;
@@ -122,6 +128,11 @@ struct fy_rm2_ctx {
     DBuf<double> out_score;
     DBuf<int64_t> out_off, out_cnt64;
     int64_t n_results = 0, users_scored = 0;
+    int32_t n_result_rows = 0;
+    DBuf<int32_t> row_user, row_cluster;
+    void* nccl_comm = nullptr;                      // ncclComm_t, attached by fy_rm2_comm_init
+    std::vector<fy_rm2_ctx*> kids;                  // n_gpus > 1: one child context per device
+    std::vector<int64_t> kid_off;
     DBuf<int32_t> p_user, p_item, p_cluster;
     DBuf<double> p_s64;
     DBuf<float> p_s32;
@@ -176,6 +187,23 @@ static int guarded(fy_rm2_ctx* ctx, F&& f) {
     }
 }
 
+// n_gpus > 1: run f on every child context, one host thread per device (each call has its own host sync points)
+template <class F>
+static int fan_out(fy_rm2_ctx* ctx, F&& f) {
+    const size_t n = ctx->kids.size();
+    std::vector<int> rc(n, FY_OK);
+    try {
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < n; i++) th.emplace_back([&, i]() { rc[i] = f(ctx->kids[i], i); });
+        for (std::thread& t : th) t.join();
+    } catch (...) {
+        return ctx->fail(FY_E_NOMEM, "could not start a host thread per device");
+    }
+    for (size_t i = 0; i < n; i++)
+        if (rc[i] != FY_OK) return ctx->fail(rc[i], "device %d: %s", ctx->kids[i]->prm.device, ctx->kids[i]->err);
+    return FY_OK;
+}
+
 extern "C" int fy_rm2_abi_version(void) { return FY_RM2_ABI_VERSION; }
 
 extern "C" void fy_rm2_default_params(fy_rm2_params* p) {
@@ -190,6 +218,8 @@ extern "C" void fy_rm2_default_params(fy_rm2_params* p) {
     p->shard_count = 1;
     p->tie_break = 0;
     p->score_mode = 0;
+    p->n_gpus = 0;
+    p->reserved = 0;
 }
 
 extern "C" int fy_rm2_create(fy_rm2_ctx** out, const fy_rm2_params* p) {
@@ -202,10 +232,24 @@ extern "C" int fy_rm2_create(fy_rm2_ctx** out, const fy_rm2_params* p) {
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || p->device < 0 || p->device >= n_dev)
         return FY_E_CUDA;            // no CPU fallback: fail loudly
+    if (p->n_gpus < 0 || p->reserved != 0) return FY_E_ARG;
+    if (p->n_gpus > 1 && (p->shard_count > 1 || p->device + p->n_gpus > n_dev)) return FY_E_ARG;
     fy_rm2_ctx* ctx = new (std::nothrow) fy_rm2_ctx();
     if (!ctx) return FY_E_NOMEM;
     ctx->prm = *p;
     if (ctx->prm.shard_count <= 0) { ctx->prm.shard_count = 1; ctx->prm.shard_rank = 0; }
+    if (p->n_gpus > 1) {                 // one child context per device; the parent only fans calls out
+        for (int i = 0; i < p->n_gpus; i++) {
+            fy_rm2_params kp = *p;
+            kp.device = p->device + i; kp.shard_rank = i; kp.shard_count = p->n_gpus; kp.n_gpus = 0;
+            fy_rm2_ctx* kid = nullptr;
+            const int rc = fy_rm2_create(&kid, &kp);
+            if (rc != FY_OK) { fy_rm2_destroy(ctx); return rc; }
+            ctx->kids.push_back(kid);
+        }
+        *out = ctx;
+        return FY_OK;
+    }
     int rc = guarded(ctx, [&]() {
         CK(cudaSetDevice(p->device));
         cudaDeviceProp prop;
@@ -222,6 +266,9 @@ extern "C" int fy_rm2_create(fy_rm2_ctx** out, const fy_rm2_params* p) {
 
 extern "C" void fy_rm2_destroy(fy_rm2_ctx* ctx) {
     if (!ctx) return;
+    for (fy_rm2_ctx* k : ctx->kids) fy_rm2_destroy(k);
+    ctx->kids.clear();
+    fy_rm2_comm_destroy(ctx);
     cudaSetDevice(ctx->prm.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
@@ -236,6 +283,7 @@ extern "C" const char* fy_rm2_last_error(const fy_rm2_ctx* ctx) { return ctx ? c
 
 extern "C" int fy_rm2_set_stream(fy_rm2_ctx* ctx, void* cuda_stream) {
     if (!ctx) return FY_E_ARG;
+    if (!ctx->kids.empty()) return ctx->fail(FY_E_UNSUPPORTED, "fy_rm2_set_stream on an n_gpus > 1 context (each device runs on its own stream)");
     return guarded(ctx, [&]() {
         CK(cudaSetDevice(ctx->prm.device));
         if (ctx->stream) CK(cudaStreamSynchronize(ctx->stream));
@@ -285,6 +333,10 @@ static int upload_ratings(fy_rm2_ctx* ctx, const int32_t* user, const int32_t* i
 extern "C" int fy_rm2_set_ratings(fy_rm2_ctx* ctx, const int32_t* user, const int32_t* item, const float* score, int64_t nnz) {
     if (!ctx) return FY_E_ARG;
     if (!user || !item || !score || nnz <= 0) return ctx->fail(FY_E_ARG, "fy_rm2_set_ratings: null pointer or nnz <= 0");
+    if (!ctx->kids.empty()) {
+        ctx->have_results = false;
+        return fan_out(ctx, [&](fy_rm2_ctx* k, size_t) { return fy_rm2_set_ratings(k, user, item, score, nnz); });
+    }
     return guarded(ctx, [&]() { ctx->use_ext = false; return upload_ratings(ctx, user, item, score, nnz); });
 }
 
@@ -374,8 +426,122 @@ extern "C" int fy_rm2_set_clustering(fy_rm2_ctx* ctx, const int32_t* user, const
     if (!ctx) return FY_E_ARG;
     if (!user || !cluster || !cluster_size || n_users <= 0 || n_clusters <= 0)
         return ctx->fail(FY_E_ARG, "fy_rm2_set_clustering: null pointer or empty input");
+    if (!ctx->kids.empty()) {
+        ctx->have_results = false;
+        ctx->n_users = (int32_t)n_users;
+        return fan_out(ctx, [&](fy_rm2_ctx* k, size_t) { return fy_rm2_set_clustering(k, user, cluster, n_users, cluster_size, n_clusters); });
+    }
     return guarded(ctx, [&]() { ctx->use_ext = false; ctx->n_splits = 1; ctx->split = 0;
                                 return upload_clustering(ctx, user, cluster, n_users, cluster_size, n_clusters, true); });
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (the process may already hold torch's bundled libnccl.so.2: same soname, same handle)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.lib) a.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.lib) return a;
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.lib, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.lib, "ncclCommInitRank");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
+        a.Broadcast = (decltype(a.Broadcast))dlsym(a.lib, "ncclBroadcast");
+        a.GroupStart = (decltype(a.GroupStart))dlsym(a.lib, "ncclGroupStart");
+        a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.lib, "ncclGroupEnd");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Broadcast && a.GroupStart && a.GroupEnd;
+        return a;
+    }();
+    return api;
+}
+}  // namespace
+
+// every rank's [rows x stride] block of (item, score) and its row counts, broadcast in place from its owner
+static int nccl_exchange(fy_rm2_ctx* ctx, int32_t stride, cudaStream_t st) {
+    NcclApi& n = nccl_api();
+    if (!n.ok) return ctx->fail(FY_E_UNSUPPORTED, "libnccl.so.2 not available");
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    const int world = ctx->prm.shard_count;
+    auto chk = [&](ncclResult_t r, const char* what) {
+        if (r != ncclSuccess) { ctx->fail(FY_E_CUDA, "NCCL error %d (%s) in %s", (int)r, n.GetErrorString ? n.GetErrorString(r) : "?", what); throw StatusFail{FY_E_CUDA}; }
+    };
+    chk(n.GroupStart(), "ncclGroupStart");
+    for (int r = 0; r < world; r++) {
+        const int32_t r0 = ctx->h_bounds[r], rows = ctx->h_bounds[r + 1] - r0;
+        if (rows <= 0) continue;
+        int32_t* pi = ctx->out_item.p + (size_t)r0 * stride;
+        double* ps = ctx->out_score.p + (size_t)r0 * stride;
+        int32_t* pc = ctx->out_count.p + r0;
+        chk(n.Broadcast(pi, pi, (size_t)rows * stride, ncclInt32, r, comm, st), "ncclBroadcast(items)");
+        chk(n.Broadcast(ps, ps, (size_t)rows * stride, ncclFloat64, r, comm, st), "ncclBroadcast(scores)");
+        chk(n.Broadcast(pc, pc, (size_t)rows, ncclInt32, r, comm, st), "ncclBroadcast(counts)");
+    }
+    chk(n.GroupEnd(), "ncclGroupEnd");
+    return FY_OK;
+}
+
+extern "C" int fy_rm2_nccl_unique_id(void* id_out) {
+    if (!id_out) return FY_E_ARG;
+    NcclApi& n = nccl_api();
+    if (!n.ok) return FY_E_UNSUPPORTED;
+    static_assert(sizeof(ncclUniqueId) == FY_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    if (n.GetUniqueId(&id) != ncclSuccess) return FY_E_CUDA;
+    std::memcpy(id_out, &id, sizeof(id));
+    return FY_OK;
+}
+
+extern "C" int fy_rm2_comm_destroy(fy_rm2_ctx* ctx) {
+    if (!ctx) return FY_E_ARG;
+    if (ctx->nccl_comm) {
+        cudaSetDevice(ctx->prm.device);
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        nccl_api().CommDestroy((ncclComm_t)ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    return FY_OK;
+}
+
+extern "C" int fy_rm2_comm_init(fy_rm2_ctx* ctx, const void* id, int32_t world, int32_t rank) {
+    if (!ctx) return FY_E_ARG;
+    if (!id || world < 1 || rank < 0 || rank >= world) return ctx->fail(FY_E_ARG, "fy_rm2_comm_init: bad argument");
+    if (!ctx->kids.empty()) return ctx->fail(FY_E_UNSUPPORTED, "fy_rm2_comm_init on an n_gpus > 1 context");
+    if (ctx->prm.shard_count != world || ctx->prm.shard_rank != rank)
+        return ctx->fail(FY_E_ARG, "communicator (rank %d of %d) does not match the context's shard (%d of %d)", rank, world, ctx->prm.shard_rank, ctx->prm.shard_count);
+    NcclApi& n = nccl_api();
+    if (!n.ok) return ctx->fail(FY_E_UNSUPPORTED, "libnccl.so.2 not available (dlopen failed)");
+    fy_rm2_comm_destroy(ctx);
+    return guarded(ctx, [&]() {
+        CK(cudaSetDevice(ctx->prm.device));
+        ncclUniqueId uid;
+        std::memcpy(&uid, id, sizeof(uid));
+        ncclComm_t comm = nullptr;
+        const ncclResult_t r = n.CommInitRank(&comm, world, uid, rank);
+        if (r != ncclSuccess) return ctx->fail(FY_E_CUDA, "ncclCommInitRank failed: %d (%s)", (int)r, n.GetErrorString ? n.GetErrorString(r) : "?");
+        ctx->nccl_comm = (void*)comm;
+        return (int)FY_OK;
+    });
+}
+
+extern "C" int fy_rm2_shard_bounds(const fy_rm2_ctx* ctx, int32_t* bounds) {
+    if (!ctx || !bounds) return FY_E_ARG;
+    if (!ctx->have_results || ctx->h_bounds.empty()) return FY_E_STATE;
+    for (size_t r = 0; r < ctx->h_bounds.size(); r++) bounds[r] = ctx->h_bounds[r];
+    return FY_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -420,26 +586,33 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     ctx->isum.need(TI); ctx->iprob.need(TI); ctx->bvec.need(TI); ctx->total.need(1);
     ctx->icount.need(KC); ctx->item_off.need((size_t)KC + 1);
     ctx->tstart.need(tab);
-    LAUNCH(ctx, k_make_keys, cdiv(nnz, 256), 256, 0, ctx->in_user.p, ctx->in_item.p, ctx->in_score.p, nnz,
-           ctx->uid_sorted.p, ctx->uid_rank.p, U, ctx->uid_table_n ? ctx->uid_table.p : (const int32_t*)nullptr, ctx->uid_table_n,
-           ctx->uid_table_min, item_bits, ctx->max_item, ctx->keys_a.p, ctx->counters.p, ctx->flags.p);
-    unsigned long long h_counters[2]; int h_flags[DF_COUNT];
+    unsigned long long h_counters[4] = {0, 0, 0, 0}; int h_flags[DF_COUNT];
     // Sharded index: with exact (dyadic) scores the global statistics need no sort, so each rank sorts and
     // indexes only the ratings of the clusters it touches (~1/N of them) instead of all of them.
-    const bool sharded_index = ctx->prm.shard_count > 1 && ctx->exact_scores && !ctx->use_ext;
+    const int world = ctx->prm.shard_count, me = ctx->prm.shard_rank;
+    const bool exact_ok = ctx->exact_scores && U <= (1 << 22) && TI <= (1 << 22);     // <= 2^22 addends per sum (k_scan_ratings)
+    const bool sharded_index = world > 1 && exact_ok && !ctx->use_ext;
     int32_t ub = 0, ue = U;
     std::vector<int32_t> h_icount_global((size_t)KC, 0);
     uint64_t* k_sorted = ctx->keys_b.p;       // (rank, item)-sorted CSR keys
     uint64_t* k_scratch = ctx->keys_a.p;
     int32_t m = 0;
+    ctx->h_bounds.assign((size_t)world + 1, 0);
+    ctx->h_bounds[world] = U;
+    unsigned long long h_bmin_bits = ~0ull;
+    int32_t rl_h = 0, rh_h = U;               // rank range of the clusters this rank touches (sharded index)
     if (sharded_index) {
         ctx->n_u.need(U); ctx->work.need(U); ctx->work_scan.need(U); ctx->c_score.need((size_t)nnz);
+        ctx->shard_dev.need((size_t)world + 3);
         CK(cudaMemsetAsync(ctx->usum.p, 0, (size_t)U * 8, st));
         CK(cudaMemsetAsync(ctx->n_u.p, 0, (size_t)U * 4, st));
         CK(cudaMemsetAsync(ctx->isum.p, 0, (size_t)TI * 8, st));
         CK(cudaMemsetAsync(ctx->tstart.p, 0xff, tab * 4, st));
-        LAUNCH(ctx, k_global_stats, cdiv(nnz, 256), 256, 0, ctx->keys_a.p, ctx->in_score.p, nnz, item_bits, ctx->rank_cluster.p,
-               TI, ctx->usum.p, ctx->n_u.p, ctx->isum.p, ctx->tstart.p);
+        // one pass over the replicated ratings: sort keys + user sums, item sums, per-cluster item presence
+        LAUNCH(ctx, k_make_keys, cdiv(nnz, 256), 256, 0, ctx->in_user.p, ctx->in_item.p, ctx->in_score.p, nnz,
+               ctx->uid_sorted.p, ctx->uid_rank.p, U, ctx->uid_table_n ? ctx->uid_table.p : (const int32_t*)nullptr, ctx->uid_table_n,
+               ctx->uid_table_min, item_bits, ctx->max_item, ctx->keys_a.p, ctx->counters.p, ctx->flags.p,
+               ctx->rank_cluster.p, TI, ctx->usum.p, ctx->n_u.p, ctx->isum.p, ctx->tstart.p);
         LAUNCH(ctx, k_total_from_usum, cdiv(U, 256), 256, 0, ctx->usum.p, ctx->n_u.p, U, ctx->counters.p + 1, ctx->flags.p);
         LAUNCH(ctx, k_cluster_item_count, KC, 256, 0, ctx->tstart.p, TI, ctx->icount.p);
         LAUNCH(ctx, k_user_work_n, cdiv(U, 256), 256, 0, ctx->n_u.p, ctx->rank_cluster.p, ctx->icount.p, U, ctx->work.p);
@@ -449,35 +622,28 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
             ctx->cub_tmp.need(tmp);
             CK(cub::DeviceScan::InclusiveSum(ctx->cub_tmp.p, tmp, ctx->work.p, ctx->work_scan.p, U, st));
         }
-        // sync A1: input errors, global item counts, work prefix -> this rank's user range
-        std::vector<double> h_scan((size_t)U);
+        // this rank's user range and the rank range of the clusters it touches, computed on the device
+        LAUNCH(ctx, k_shard_bounds, 1, std::max(32, ((world + 1 + 31) / 32) * 32), 0, ctx->work_scan.p, U, world, me,
+               ctx->rank_cluster.p, ctx->cstart.p, ctx->shard_dev.p);
+        LAUNCH(ctx, k_compact_local, cdiv(nnz, 256), 256, 0, ctx->keys_a.p, ctx->in_score.p, nnz, item_bits,
+               ctx->shard_dev.p + world + 1, ctx->keys_b.p, ctx->c_score.p, ctx->counters.p + 3);
+        LAUNCH(ctx, k_item_prob_isum, cdiv(TI, 128), 128, 0, ctx->isum.p, TI, ctx->counters.p + 1, lambda,
+               ctx->iprob.p, ctx->bvec.p, ctx->total.p, ctx->counters.p + 2);
+        // sync A (the only one of the index phase): input errors, global item counts, every rank's range, local rating count
+        std::vector<int32_t> h_shard((size_t)world + 3);
         CK(cudaMemcpyAsync(h_counters, ctx->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h_flags, ctx->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h_icount_global.data(), ctx->icount.p, (size_t)KC * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(h_scan.data(), ctx->work_scan.p, (size_t)U * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_shard.data(), ctx->shard_dev.p, h_shard.size() * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ctx->h_total, ctx->total.p, sizeof(double), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         { int rc = check_flags(ctx, h_flags); if (rc != FY_OK) return rc; }
         if (h_counters[0] == 0) return ctx->fail(FY_E_ARG, "no positive rating");
-        const double tot = h_scan[U - 1];
-        auto bound = [&](int r) -> int32_t {
-            if (r <= 0) return 0;
-            if (r >= ctx->prm.shard_count) return U;
-            const double target = tot * (double)r / (double)ctx->prm.shard_count;
-            return (int32_t)(std::lower_bound(h_scan.begin(), h_scan.end(), target) - h_scan.begin());
-        };
-        ub = bound(ctx->prm.shard_rank);
-        ue = bound(ctx->prm.shard_rank + 1);
-        int32_t rl = 0, rh = 0;                                 // rank range of the touched clusters
-        if (ue > ub) {
-            rl = ctx->h_cstart[ctx->h_rank_cluster[ub]];
-            rh = ctx->h_cstart[ctx->h_rank_cluster[ue - 1] + 1];
-        }
-        LAUNCH(ctx, k_compact_local, cdiv(nnz, 256), 256, 0, ctx->keys_a.p, ctx->in_score.p, nnz, item_bits, rl, rh,
-               ctx->keys_b.p, ctx->c_score.p, ctx->counters.p + 3);
-        unsigned long long h_m = 0;
-        CK(cudaMemcpyAsync(&h_m, ctx->counters.p + 3, sizeof(h_m), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));                          // sync A2: number of local ratings
-        m = (int32_t)h_m;
+        for (int r = 0; r <= world; r++) ctx->h_bounds[r] = h_shard[r];
+        ub = h_shard[me]; ue = h_shard[me + 1];
+        rl_h = h_shard[world + 1]; rh_h = h_shard[world + 2];
+        h_bmin_bits = h_counters[2];
+        m = (int32_t)h_counters[3];
         if (m > 0) {
             size_t tmp = 0;
             CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->keys_b.p, ctx->keys_a.p, ctx->c_score.p, ctx->s_score.p,
@@ -488,6 +654,10 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
         }
         k_sorted = ctx->keys_a.p; k_scratch = ctx->keys_b.p;
     } else {
+        LAUNCH(ctx, k_make_keys, cdiv(nnz, 256), 256, 0, ctx->in_user.p, ctx->in_item.p, ctx->in_score.p, nnz,
+               ctx->uid_sorted.p, ctx->uid_rank.p, U, ctx->uid_table_n ? ctx->uid_table.p : (const int32_t*)nullptr, ctx->uid_table_n,
+               ctx->uid_table_min, item_bits, ctx->max_item, ctx->keys_a.p, ctx->counters.p, ctx->flags.p,
+               (const int32_t*)nullptr, TI, (double*)nullptr, (int32_t*)nullptr, (double*)nullptr, (int32_t*)nullptr);
         size_t tmp = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->keys_a.p, ctx->keys_b.p, ctx->in_score.p, ctx->s_score.p,
                                            (int64_t)nnz, 0, key_bits, st));
@@ -495,7 +665,7 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
         CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, ctx->keys_a.p, ctx->keys_b.p, ctx->in_score.p, ctx->s_score.p,
                                            (int64_t)nnz, 0, key_bits, st));
         // sync A: number of positive ratings, input errors
-        CK(cudaMemcpyAsync(h_counters, ctx->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_counters, ctx->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h_flags, ctx->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         { int rc = check_flags(ctx, h_flags); if (rc != FY_OK) return rc; }
@@ -533,9 +703,8 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     if (m > 0) LAUNCH(ctx, k_item_groups, cdiv(m, 256), 256, 0, keys2, m, rank_bits, ctx->rank_cluster.p, TI,
                       ctx->ifirst.p, ctx->ilast.p, ctx->tstart.p, ctx->tend.p);
     if (sharded_index) {
-        LAUNCH(ctx, k_item_prob_isum, cdiv(TI, 128), 128, 0, ctx->isum.p, TI, ctx->counters.p + 1, lambda,
-               ctx->iprob.p, ctx->bvec.p, ctx->total.p, ctx->counters.p + 2);
-    } else if (ctx->exact_scores && !ctx->use_ext) {
+        // p(i|C), b and the total were computed from the global item sums before the compaction
+    } else if (exact_ok && !ctx->use_ext) {
         ctx->tsum.need(tab);
         LAUNCH(ctx, k_group_sum, cdiv((int64_t)tab, 256), 256, 0, ctx->tstart.p, ctx->tend.p, ctx->csc_src.p, ctx->s_score.p, tab, ctx->tsum.p);
         LAUNCH(ctx, k_item_prob_fast, cdiv(TI, 128), 128, 0, ctx->tsum.p, KC, TI, ctx->counters.p + 1, lambda,
@@ -558,36 +727,41 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
         CK(cub::DeviceScan::InclusiveSum(ctx->cub_tmp.p, tmp, ctx->work.p, ctx->work_scan.p, U, st));
     }
 
-    // sync B: per-cluster item counts, total, flags, (work prefix)
-    ctx->h_icount.resize(KC); ctx->h_item_off.resize((size_t)KC + 1);
-    std::vector<double> h_scan;
-    CK(cudaMemcpyAsync(ctx->h_icount.data(), ctx->icount.p, (size_t)KC * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(ctx->h_item_off.data(), ctx->item_off.p, ((size_t)KC + 1) * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&ctx->h_total, ctx->total.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-    unsigned long long h_bmin_bits = 0;
-    CK(cudaMemcpyAsync(&h_bmin_bits, ctx->counters.p + 2, sizeof(h_bmin_bits), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_flags, ctx->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
-    if (ctx->prm.shard_count > 1 && !sharded_index) {
-        h_scan.resize(U);
-        CK(cudaMemcpyAsync(h_scan.data(), ctx->work_scan.p, (size_t)U * 8, cudaMemcpyDeviceToHost, st));
+    ctx->h_icount.assign(KC, 0); ctx->h_item_off.assign((size_t)KC + 1, 0);
+    if (sharded_index) {
+        // no sync: the touched clusters hold all their users' ratings, so their item counts are the global ones
+        for (int32_t c = 0; c < KC; c++) {
+            const int32_t cs = ctx->h_cstart[c], ce = ctx->h_cstart[c + 1];
+            const bool touched = ce > cs && cs >= rl_h && ce <= rh_h;
+            ctx->h_icount[c] = touched ? h_icount_global[c] : 0;
+            ctx->h_item_off[c + 1] = ctx->h_item_off[c] + ctx->h_icount[c];
+        }
+    } else {
+        // sync B: per-cluster item counts, total, flags, (work prefix)
+        std::vector<double> h_scan;
+        CK(cudaMemcpyAsync(ctx->h_icount.data(), ctx->icount.p, (size_t)KC * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_item_off.data(), ctx->item_off.p, ((size_t)KC + 1) * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ctx->h_total, ctx->total.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h_bmin_bits, ctx->counters.p + 2, sizeof(h_bmin_bits), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_flags, ctx->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+        if (world > 1) {
+            h_scan.resize(U);
+            CK(cudaMemcpyAsync(h_scan.data(), ctx->work_scan.p, (size_t)U * 8, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        { int rc = check_flags(ctx, h_flags); if (rc != FY_OK) return rc; }
+        for (int32_t c = 0; c < KC; c++) h_icount_global[c] = ctx->h_icount[c];
+        // shard = contiguous range of user ranks with ~equal estimated work (n_u * I_c)
+        if (world > 1) {
+            const double tot = h_scan[U - 1];
+            for (int r = 1; r < world; r++) {
+                const double target = tot * (double)r / (double)world;
+                ctx->h_bounds[r] = (int32_t)(std::lower_bound(h_scan.begin(), h_scan.end(), target) - h_scan.begin());
+            }
+            ub = ctx->h_bounds[me]; ue = ctx->h_bounds[me + 1];
+        }
     }
-    CK(cudaStreamSynchronize(st));
-    { int rc = check_flags(ctx, h_flags); if (rc != FY_OK) return rc; }
     const int32_t n_slots = ctx->h_item_off[KC];
-
-    // shard = contiguous range of user ranks with ~equal estimated work (n_u * I_c)
-    if (!sharded_index) for (int32_t c = 0; c < KC; c++) h_icount_global[c] = ctx->h_icount[c];
-    if (ctx->prm.shard_count > 1 && !sharded_index) {
-        const double tot = h_scan[U - 1];
-        auto bound = [&](int r) -> int32_t {
-            if (r <= 0) return 0;
-            if (r >= ctx->prm.shard_count) return U;
-            const double target = tot * (double)r / (double)ctx->prm.shard_count;
-            return (int32_t)(std::lower_bound(h_scan.begin(), h_scan.end(), target) - h_scan.begin());
-        };
-        ub = bound(ctx->prm.shard_rank);
-        ue = bound(ctx->prm.shard_rank + 1);
-    }
     ctx->shard_begin = ub; ctx->shard_end = ue;
 
     // ---------------- local item numbering, d, alpha, c(u,j) ----------------
@@ -604,12 +778,7 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
                ctx->csr_delta.p, ctx->csc_lu.p, ctx->csc_delta.p);
     }
     ctx->cbound.need((size_t)KC * 3);
-    {
-        std::vector<unsigned long long> init((size_t)KC * 3);
-        for (int32_t c = 0; c < KC; c++) { init[3 * c] = 0; init[3 * c + 1] = 0; init[3 * c + 2] = ~0ull; }
-        CK(cudaMemcpyAsync(ctx->cbound.p, init.data(), init.size() * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));      // `init` dies at the end of this block
-    }
+    LAUNCH(ctx, k_init_cbound, cdiv(KC, 128), 128, 0, ctx->cbound.p, KC);
     if (n_slots > 0)
         LAUNCH(ctx, k_alpha_cuj, cdiv((int64_t)n_slots * 32, 256), 256, 0, ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, keys2, rank_bits,
                ctx->rank_cluster.p, ctx->cstart.p, ctx->csc_src.p, ctx->csc_delta.p, n_slots, ctx->c_alpha.p, ctx->csr_c.p,
@@ -650,11 +819,16 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     // min(N, I_c) beyond the shared-memory select/sort bound: whole-row stable segmented sort (exact stream)
     const bool big_n = out_stride > TOPN_MAX_SELECT;
     ctx->out_stride = out_stride;
-    ctx->out_item.need((size_t)std::max(n_rows, 1) * out_stride);
-    ctx->out_score.need((size_t)std::max(n_rows, 1) * out_stride);
-    ctx->out_count.need((size_t)std::max(n_rows, 1) + 1);
-    ctx->out_off.need((size_t)std::max(n_rows, 1) + 1);
-    CK(cudaMemsetAsync(ctx->out_count.p, 0, ((size_t)std::max(n_rows, 1) + 1) * 4, st));
+    // With a communicator attached (fy_rm2_comm_init) the dense [row x N] result blocks of all ranks live in one buffer
+    // indexed by global user rank and are exchanged in place at the end of the run; otherwise only this shard's rows exist.
+    const bool gather_on = ctx->nccl_comm != nullptr && world > 1;
+    const int32_t ob = gather_on ? 0 : ub;                   // user rank of output row 0
+    const int32_t rows_total = gather_on ? U : n_rows;
+    ctx->out_item.need((size_t)std::max(rows_total, 1) * out_stride);
+    ctx->out_score.need((size_t)std::max(rows_total, 1) * out_stride);
+    ctx->out_count.need((size_t)std::max(rows_total, 1) + 1);
+    ctx->out_off.need((size_t)std::max(rows_total, 1) + 1);
+    CK(cudaMemsetAsync(ctx->out_count.p, 0, ((size_t)std::max(rows_total, 1) + 1) * 4, st));
     const double log_items = std::log((double)ctx->prm.number_of_items);   // AbstractRM2Reducer.java:328
 
     // auto mode: approximate stream over the hi-word plane + exact re-score of the candidates
@@ -669,7 +843,9 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     if (use_hi && !ctx->use_ext) {
         std::vector<unsigned long long> hb((size_t)KC * 3);
         CK(cudaMemcpyAsync(hb.data(), ctx->cbound.p, hb.size() * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));      // sync B2: per-cluster bounds on alpha and b
+        CK(cudaMemcpyAsync(h_flags, ctx->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));      // sync B2: per-cluster bounds on alpha and b (+ duplicate-rating flag of the local sort)
+        { int rc = check_flags(ctx, h_flags); if (rc != FY_OK) return rc; }
         for (int32_t c = 0; c < KC; c++) {
             double a_max, b_max, b_min;
             std::memcpy(&a_max, &hb[3 * c], 8); std::memcpy(&b_max, &hb[3 * c + 1], 8);
@@ -892,7 +1068,7 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
                 if (tmp > ctx->sort_tmp.cap) { CK(cudaStreamSynchronize(sT)); ctx->sort_tmp.need(tmp); }
                 CK(cub::DeviceSegmentedSort::StableSortPairs(ctx->sort_tmp.p, tmp, ctx->sort_keys[0].p, ctx->sort_keys[1].p, ctx->sort_idx[0].p,
                                                              ctx->sort_idx[1].p, tot, nb, ctx->seg_off.p, ctx->seg_off.p + 1, sT));
-                LAUNCH_ON(ctx, sT, k_emit_sorted, nb, 256, 0, ctx->sort_keys[1].p, ctx->sort_idx[1].p, ctx->ustat[sb].p, ld, b0, ub, slot0,
+                LAUNCH_ON(ctx, sT, k_emit_sorted, nb, 256, 0, ctx->sort_keys[1].p, ctx->sort_idx[1].p, ctx->ustat[sb].p, ld, b0, ob, slot0,
                           ctx->prm.top_n, out_stride, ctx->prm.filter_users, ctx->split, ctx->n_splits, ctx->rank_userid.p,
                           ctx->c_item.p, ctx->out_item.p, ctx->out_score.p, ctx->out_count.p);
                 seg_end(k, sT);
@@ -900,7 +1076,7 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
                 const size_t k = seg_begin(SEG_TOPN, sT);
                 LAUNCH_ON(ctx, sT, k_topn, nb, TOPN_THREADS, topn_smem, ctx->scores[sb].p, ctx->ustat[sb].p, I_c, ld, b0, slot0,
                           ctx->prm.top_n, out_stride, ctx->prm.filter_users, ctx->split, ctx->n_splits, ctx->rank_userid.p,
-                          ctx->c_item.p, b0 - ub, ctx->out_item.p, ctx->out_score.p, ctx->out_count.p,
+                          ctx->c_item.p, b0 - ob, ctx->out_item.p, ctx->out_score.p, ctx->out_count.p,
                           ctx->rowptr.p, cap, plan[c].mode == 2 ? 2.5e-7 : 4.8e-7, use_hi ? ctx->cand[sb].p : (int32_t*)nullptr,
                           use_hi ? ctx->cand_cnt[sb].p : (int32_t*)nullptr, ctx->overflow.p);
                 seg_end(k, sT);
@@ -910,7 +1086,7 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
                 LAUNCH_ON(ctx, sT, k_refine_score, dim3(nb, cdiv(cap, REFINE_THREADS / 32)), REFINE_THREADS, 0, ctx->H[hb].p, ld, b0,
                           slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, log_items, log_K, cap, ctx->cand[sb].p,
                           ctx->cand_cnt[sb].p, ctx->cand_score[sb].p);
-                LAUNCH_ON(ctx, sT, k_refine_sort, nb, REFINE_THREADS, (size_t)cap * 12, b0, ub, slot0, ctx->c_item.p, cap,
+                LAUNCH_ON(ctx, sT, k_refine_sort, nb, REFINE_THREADS, (size_t)cap * 12, b0, ob, slot0, ctx->c_item.p, cap,
                           ctx->cand[sb].p, ctx->cand_cnt[sb].p, ctx->cand_score[sb].p, out_stride, ctx->out_item.p,
                           ctx->out_score.p, ctx->out_count.p);
                 seg_end(k, sT);
@@ -926,44 +1102,59 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     CK(cudaEventRecord(evJoin, sG)); CK(cudaStreamWaitEvent(st, evJoin, 0));
     CK(cudaEventRecord(evFork, sT)); CK(cudaStreamWaitEvent(st, evFork, 0));
 
-    // ---------------- pack ----------------
-    if (n_rows > 0) {
-        size_t tmp = 0;
-        ctx->out_cnt64.need((size_t)n_rows + 1);
-        LAUNCH(ctx, k_widen_counts, cdiv(n_rows + 1, 256), 256, 0, ctx->out_count.p, n_rows + 1, ctx->out_cnt64.p);
-        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->out_cnt64.p, ctx->out_off.p, n_rows + 1, st));
-        ctx->cub_tmp.need(tmp);
-        CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, ctx->out_cnt64.p, ctx->out_off.p, n_rows + 1, st));
-    }
-    int64_t total_out = 0;
-    if (n_rows > 0) CK(cudaMemcpyAsync(&total_out, ctx->out_off.p + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    // sync C1: did a candidate list overflow?  (decided before the exchange: every rank enters the collective exactly once)
     int h_overflow = 0;
     CK(cudaMemcpyAsync(&h_overflow, ctx->overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));   // sync C: number of result triples
-    if (use_hi && h_overflow > 0) return 1;      // a candidate list overflowed: redo in exact mode (rare)
-    ctx->n_results = total_out;
-    ctx->p_user.need((size_t)total_out); ctx->p_item.need((size_t)total_out); ctx->p_cluster.need((size_t)total_out);
-    ctx->p_s64.need((size_t)total_out); ctx->p_s32.need((size_t)total_out);
-    if (n_rows > 0 && total_out > 0)
-        LAUNCH(ctx, k_pack, n_rows, 128, 0, ctx->out_item.p, ctx->out_score.p, ctx->out_count.p, ctx->out_off.p, out_stride,
-               ub, n_rows, ctx->rank_userid.p, ctx->rank_cluster.p, ctx->p_user.p, ctx->p_item.p, ctx->p_s64.p, ctx->p_s32.p,
-               ctx->p_cluster.p);
-    CK(cudaEventRecord(ev_end, st));
-
-    // users scored + work figures
-    std::vector<int32_t> h_count((size_t)std::max(n_rows, 1));
-    std::vector<int32_t> h_rowptr((size_t)U + 1);
-    if (n_rows > 0) CK(cudaMemcpyAsync(h_count.data(), ctx->out_count.p, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_rowptr.data(), ctx->rowptr.p, ((size_t)U + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_flags, ctx->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    ctx->users_scored = 0;
-    double terms = 0.0;
-    for (int32_t r = 0; r < n_rows; r++) {
-        if (h_count[r] > 0) ctx->users_scored++;
-        const int32_t rank = ub + r;
-        terms += (double)(h_rowptr[rank + 1] - h_rowptr[rank]) * (double)ctx->h_icount[ctx->h_rank_cluster[rank]];
+    { int rc = check_flags(ctx, h_flags); if (rc != FY_OK) return rc; }
+    if (use_hi && h_overflow > 0) return 1;      // redo in exact mode (rare)
+
+    // ---------------- exchange: every rank ends with the top-N blocks of all users (north_star: "NCCL ... to gather the
+    // final top-N lists"); one grouped in-place broadcast per rank and array, issued from here on the run's stream ----------------
+    cudaEvent_t ev_gather0 = ctx->ev(evi++), ev_gather1 = ctx->ev(evi++);
+    CK(cudaEventRecord(ev_gather0, st));
+    if (gather_on) {
+        int rc = nccl_exchange(ctx, out_stride, st);
+        if (rc != FY_OK) return rc;
     }
+    CK(cudaEventRecord(ev_gather1, st));
+
+    // ---------------- pack ----------------
+    ctx->counters.need(8); ctx->run_terms.need(1);
+    CK(cudaMemsetAsync(ctx->counters.p + 4, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctx->run_terms.p, 0, sizeof(double), st));
+    const size_t bound_out = (size_t)std::max(rows_total, 1) * out_stride;
+    ctx->p_user.need(bound_out); ctx->p_item.need(bound_out); ctx->p_cluster.need(bound_out);
+    ctx->p_s64.need(bound_out); ctx->p_s32.need(bound_out);
+    ctx->row_user.need((size_t)std::max(rows_total, 1)); ctx->row_cluster.need((size_t)std::max(rows_total, 1));
+    if (rows_total > 0) {
+        size_t tmp = 0;
+        ctx->out_cnt64.need((size_t)rows_total + 1);
+        LAUNCH(ctx, k_widen_counts, cdiv(rows_total + 1, 256), 256, 0, ctx->out_count.p, rows_total + 1, ctx->out_cnt64.p);
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->out_cnt64.p, ctx->out_off.p, rows_total + 1, st));
+        ctx->cub_tmp.need(tmp);
+        CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, ctx->out_cnt64.p, ctx->out_off.p, rows_total + 1, st));
+        LAUNCH(ctx, k_pack, rows_total, 128, 0, ctx->out_item.p, ctx->out_score.p, ctx->out_count.p, ctx->out_off.p, out_stride,
+               ob, rows_total, ctx->rank_userid.p, ctx->rank_cluster.p, ctx->p_user.p, ctx->p_item.p, ctx->p_s64.p, ctx->p_s32.p,
+               ctx->p_cluster.p, ctx->row_user.p, ctx->row_cluster.p);
+    }
+    if (n_rows > 0)      // users scored and log-terms of THIS shard, reduced on the device
+        LAUNCH(ctx, k_run_totals, cdiv(n_rows, 256), 256, 0, ctx->out_count.p + (ub - ob), ctx->work.p + ub, n_rows,
+               ctx->counters.p + 4, ctx->run_terms.p);
+    CK(cudaEventRecord(ev_end, st));
+    int64_t total_out = 0;
+    unsigned long long h_users = 0;
+    double terms = 0.0;
+    if (rows_total > 0) CK(cudaMemcpyAsync(&total_out, ctx->out_off.p + rows_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h_users, ctx->counters.p + 4, sizeof(h_users), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&terms, ctx->run_terms.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));   // sync C2: number of result triples, users scored, work figures
+    ctx->n_results = total_out;
+    ctx->n_result_rows = rows_total;
+    ctx->users_scored = (int64_t)h_users;
     float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev_gather0, ev_gather1)); ctx->prof.ms_gather = ms;
     CK(cudaEventElapsedTime(&ms, ev_start, ev_end)); ctx->prof.ms_total = ms;
     CK(cudaEventElapsedTime(&ms, ev_start, ev_index)); ctx->prof.ms_index = ms;
     for (const Seg& g : segs) {
@@ -989,14 +1180,46 @@ static int run_pipeline(fy_rm2_ctx* ctx) {
 
 extern "C" int fy_rm2_run(fy_rm2_ctx* ctx) {
     if (!ctx) return FY_E_ARG;
+    if (!ctx->kids.empty()) {
+        ctx->have_results = false;
+        const int rc = fan_out(ctx, [&](fy_rm2_ctx* k, size_t) { return fy_rm2_run(k); });
+        if (rc != FY_OK) return rc;
+        // shards are contiguous ranges of the (cluster, user id) order: concatenating them in shard order keeps it
+        ctx->kid_off.assign(ctx->kids.size() + 1, 0);
+        ctx->users_scored = 0; ctx->n_result_rows = 0;
+        fy_rm2_profile agg{};
+        for (size_t i = 0; i < ctx->kids.size(); i++) {
+            const fy_rm2_ctx* k = ctx->kids[i];
+            ctx->kid_off[i + 1] = ctx->kid_off[i] + k->n_results;
+            ctx->users_scored += k->users_scored;
+            ctx->n_result_rows += k->n_result_rows;
+            const fy_rm2_profile& q = k->prof;
+            agg.ms_total = std::max(agg.ms_total, q.ms_total); agg.ms_index = std::max(agg.ms_index, q.ms_index);
+            agg.ms_gram = std::max(agg.ms_gram, q.ms_gram); agg.ms_score = std::max(agg.ms_score, q.ms_score);
+            agg.ms_topn = std::max(agg.ms_topn, q.ms_topn); agg.ms_refine = std::max(agg.ms_refine, q.ms_refine);
+            agg.log_terms += q.log_terms; agg.score_bytes += q.score_bytes; agg.gram_bytes += q.gram_bytes;
+            agg.users_scored += q.users_scored; agg.kernel_launches += q.kernel_launches;
+            agg.clusters_touched += q.clusters_touched; agg.score_launches += q.score_launches;
+            agg.bytes_per_term = q.bytes_per_term; agg.exact_rerun = std::max(agg.exact_rerun, q.exact_rerun);
+            agg.score_kernel = std::max(agg.score_kernel, q.score_kernel);
+        }
+        ctx->prof = agg;
+        ctx->n_results = ctx->kid_off.back();
+        ctx->have_results = true;
+        return FY_OK;
+    }
     return guarded(ctx, [&]() { return run_pipeline(ctx); });
 }
 
-extern "C" int32_t fy_rm2_max_item(const fy_rm2_ctx* ctx) { return ctx ? ctx->max_item : -1; }
+extern "C" int32_t fy_rm2_max_item(const fy_rm2_ctx* ctx) { return !ctx ? -1 : (ctx->kids.empty() ? ctx->max_item : ctx->kids[0]->max_item); }
 
 extern "C" int fy_rm2_stats(fy_rm2_ctx* ctx, double* user_sum, double* item_prob, double* total) {
     if (!ctx) return FY_E_ARG;
     if (!ctx->have_results) return ctx->fail(FY_E_STATE, "fy_rm2_stats needs a successful fy_rm2_run");
+    if (!ctx->kids.empty()) {            // the statistics are global: every device holds the same ones
+        const int rc = fy_rm2_stats(ctx->kids[0], user_sum, item_prob, total);
+        return rc == FY_OK ? rc : ctx->fail(rc, "%s", ctx->kids[0]->err);
+    }
     return guarded(ctx, [&]() {
         CK(cudaSetDevice(ctx->prm.device));
         if (user_sum) {
@@ -1020,6 +1243,12 @@ extern "C" int64_t fy_rm2_users_scored(const fy_rm2_ctx* ctx) { return (ctx && c
 extern "C" int fy_rm2_results(fy_rm2_ctx* ctx, int32_t* user, int32_t* item, double* score64, float* score32, int32_t* cluster) {
     if (!ctx) return FY_E_ARG;
     if (!ctx->have_results) return ctx->fail(FY_E_STATE, "fy_rm2_results needs a successful fy_rm2_run");
+    if (!ctx->kids.empty())              // every device copies its slice straight into the caller's buffers, in parallel
+        return fan_out(ctx, [&](fy_rm2_ctx* k, size_t i) {
+            const int64_t o = ctx->kid_off[i];
+            return fy_rm2_results(k, user ? user + o : nullptr, item ? item + o : nullptr, score64 ? score64 + o : nullptr,
+                                  score32 ? score32 + o : nullptr, cluster ? cluster + o : nullptr);
+        });
     return guarded(ctx, [&]() {
         CK(cudaSetDevice(ctx->prm.device));
         const size_t n = (size_t)ctx->n_results;
@@ -1040,12 +1269,69 @@ extern "C" int fy_rm2_results_device(fy_rm2_ctx* ctx, const int32_t** user, cons
                                      const float** score32, const int32_t** cluster) {
     if (!ctx) return FY_E_ARG;
     if (!ctx->have_results) return ctx->fail(FY_E_STATE, "fy_rm2_results_device needs a successful fy_rm2_run");
+    if (!ctx->kids.empty()) return ctx->fail(FY_E_UNSUPPORTED, "fy_rm2_results_device on an n_gpus > 1 context (results live on several devices)");
     if (user) *user = ctx->p_user.p;
     if (item) *item = ctx->p_item.p;
     if (score64) *score64 = ctx->p_s64.p;
     if (score32) *score32 = ctx->p_s32.p;
     if (cluster) *cluster = ctx->p_cluster.p;
     return FY_OK;
+}
+
+extern "C" int64_t fy_rm2_result_row_count(const fy_rm2_ctx* ctx) { return (ctx && ctx->have_results) ? ctx->n_result_rows : -1; }
+
+extern "C" int fy_rm2_result_rows(fy_rm2_ctx* ctx, int32_t* user, int32_t* cluster, int32_t* count) {
+    if (!ctx) return FY_E_ARG;
+    if (!ctx->have_results) return ctx->fail(FY_E_STATE, "fy_rm2_result_rows needs a successful fy_rm2_run");
+    if (!ctx->kids.empty()) {
+        std::vector<int64_t> ro(ctx->kids.size() + 1, 0);
+        for (size_t i = 0; i < ctx->kids.size(); i++) ro[i + 1] = ro[i] + ctx->kids[i]->n_result_rows;
+        return fan_out(ctx, [&](fy_rm2_ctx* k, size_t i) {
+            return fy_rm2_result_rows(k, user ? user + ro[i] : nullptr, cluster ? cluster + ro[i] : nullptr, count ? count + ro[i] : nullptr);
+        });
+    }
+    return guarded(ctx, [&]() {
+        CK(cudaSetDevice(ctx->prm.device));
+        const size_t n = (size_t)ctx->n_result_rows;
+        cudaStream_t st = ctx->stream;
+        if (n) {
+            if (user) CK(cudaMemcpyAsync(user, ctx->row_user.p, n * 4, cudaMemcpyDeviceToHost, st));
+            if (cluster) CK(cudaMemcpyAsync(cluster, ctx->row_cluster.p, n * 4, cudaMemcpyDeviceToHost, st));
+            if (count) CK(cudaMemcpyAsync(count, ctx->out_count.p, n * 4, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        return (int)FY_OK;
+    });
+}
+
+// Roofline probe (see k_probe_plane_read): GB/s the L2 -> SM path delivers for the score kernel's access pattern.
+extern "C" int fy_rm2_probe_plane_read(fy_rm2_ctx* ctx, int32_t n_rows, int32_t n_users, int32_t rows_per_user, int32_t reps,
+                                       double* gb_per_s, double* ms_per_launch) {
+    if (!ctx || n_rows <= 0 || n_users <= 0 || rows_per_user <= 0 || reps <= 0) return FY_E_ARG;
+    if (!ctx->kids.empty()) return ctx->fail(FY_E_UNSUPPORTED, "not available on an n_gpus > 1 context");
+    return guarded(ctx, [&]() {
+        using namespace fy;
+        CK(cudaSetDevice(ctx->prm.device));
+        cudaStream_t st = ctx->stream;
+        const int32_t ld = cdiv(n_rows, SCOREH_TILE) * SCOREH_TILE;
+        DBuf<uint32_t> plane, sink;
+        plane.need((size_t)n_rows * ld); sink.need(4);
+        CK(cudaMemsetAsync(plane.p, 0x3f, (size_t)n_rows * ld * 4, st));
+        const int32_t rpu = cdiv(rows_per_user, 8) * 8;
+        const dim3 grid(n_users, ld / SCOREH_TILE);
+        LAUNCH(ctx, k_probe_plane_read, grid, SCORE_THREADS, 0, plane.p, n_rows, ld, rpu, sink.p);      // warm-up
+        cudaEvent_t e0 = ctx->ev(0), e1 = ctx->ev(1);
+        CK(cudaEventRecord(e0, st));
+        for (int r = 0; r < reps; r++) LAUNCH(ctx, k_probe_plane_read, grid, SCORE_THREADS, 0, plane.p, n_rows, ld, rpu, sink.p);
+        CK(cudaEventRecord(e1, st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double bytes = (double)n_users * ld * 4.0 * rpu;
+        if (ms_per_launch) *ms_per_launch = ms / reps;
+        if (gb_per_s) *gb_per_s = bytes * reps / (ms * 1e-3) / 1e9;
+        return (int)FY_OK;
+    });
 }
 
 extern "C" int fy_rm2_get_profile(const fy_rm2_ctx* ctx, fy_rm2_profile* out) {
@@ -1065,7 +1351,7 @@ extern "C" int fy_rm2_score_group(fy_rm2_ctx* ctx, int32_t cluster_id, int32_t s
     if (!group_user || !group_user_sum || !r_user || !r_item || !r_score || !item_prob || n_group_users <= 0 || nnz <= 0 ||
         n_splits <= 0 || split < 0 || split >= n_splits || cluster_id < 0 || max_item < 0)
         return ctx->fail(FY_E_ARG, "fy_rm2_score_group: bad argument");
-    if (ctx->prm.shard_count > 1) return ctx->fail(FY_E_UNSUPPORTED, "fy_rm2_score_group on a sharded context");
+    if (ctx->prm.shard_count > 1 || !ctx->kids.empty()) return ctx->fail(FY_E_UNSUPPORTED, "fy_rm2_score_group on a sharded / n_gpus > 1 context");
     return guarded(ctx, [&]() {
         int rc = upload_ratings(ctx, r_user, r_item, r_score, nnz);
         if (rc != FY_OK) return rc;
@@ -1089,6 +1375,7 @@ extern "C" int fy_rm2_score_group(fy_rm2_ctx* ctx, int32_t cluster_id, int32_t s
         if (ctx->n_results > 0) {
             std::vector<int32_t> cid((size_t)ctx->n_results, cluster_id);
             CK(cudaMemcpyAsync(ctx->p_cluster.p, cid.data(), (size_t)ctx->n_results * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->row_cluster.p, cid.data(), (size_t)std::min<int64_t>(ctx->n_result_rows, ctx->n_results) * 4, cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
         }
         return (int)FY_OK;
@@ -1103,6 +1390,7 @@ extern "C" int fyi_cooc_gemm_launch(const uint8_t* Bt, int n_items, int k_pad, i
 
 extern "C" int fy_cooc_counts(fy_rm2_ctx* ctx, int32_t n_user_ids, int32_t n_items, int32_t* counts_out, double* ms_gemm_out) {
     if (!ctx) return FY_E_ARG;
+    if (!ctx->kids.empty()) return ctx->fail(FY_E_UNSUPPORTED, "not available on an n_gpus > 1 context");
     if (!ctx->have_ratings) return ctx->fail(FY_E_STATE, "fy_cooc_counts needs fy_rm2_set_ratings first");
     if (n_user_ids <= 0 || n_items <= ctx->max_item) return ctx->fail(FY_E_ARG, "n_items must exceed the largest rated item id (%d)", ctx->max_item);
     return guarded(ctx, [&]() {
@@ -1150,6 +1438,7 @@ extern "C" int fyi_gemm_u8_nt(const uint8_t* A, int a_rows, const uint8_t* B, in
 extern "C" int fy_knn_neighbours(fy_rm2_ctx* ctx, int32_t n_user_ids, int32_t n_items, int32_t k,
                                  int32_t* neighbour_out, int32_t* count_out, int32_t* n_out, double* ms_gemm_out) {
     if (!ctx) return FY_E_ARG;
+    if (!ctx->kids.empty()) return ctx->fail(FY_E_UNSUPPORTED, "not available on an n_gpus > 1 context");
     if (!ctx->have_ratings) return ctx->fail(FY_E_STATE, "fy_knn_neighbours needs fy_rm2_set_ratings first");
     if (!neighbour_out || n_user_ids <= 0 || n_items <= ctx->max_item) return ctx->fail(FY_E_ARG, "bad argument (n_items must exceed the largest rated item id %d)", ctx->max_item);
     if (k <= 0 || k > fy::TOPN_MAX_SELECT) return ctx->fail(FY_E_UNSUPPORTED, "k outside [1, %d]", fy::TOPN_MAX_SELECT);

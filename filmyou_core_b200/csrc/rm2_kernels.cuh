@@ -58,7 +58,10 @@ __global__ void k_make_keys(const int32_t* __restrict__ r_user, const int32_t* _
                             int32_t n_users, const int32_t* __restrict__ uid_table, int32_t uid_table_n, int32_t uid_table_min,
                             int item_bits, int32_t max_item_allowed,
                             uint64_t* __restrict__ keys, unsigned long long* __restrict__ n_valid,
-                            int* __restrict__ flags) {
+                            int* __restrict__ flags,
+                            // optional (sharded index, exact scores): the global statistics in the same pass
+                            const int32_t* __restrict__ rank_cluster, int32_t table_items, double* __restrict__ usum,
+                            int32_t* __restrict__ n_u, double* __restrict__ isum, int32_t* __restrict__ present) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int local_valid = 0;
     if (e < nnz) {
@@ -86,6 +89,13 @@ __global__ void k_make_keys(const int32_t* __restrict__ r_user, const int32_t* _
             } else {
                 key = ((uint64_t)(uint32_t)rank << item_bits) | (uint64_t)(uint32_t)it;
                 local_valid = 1;
+                if (usum) {
+                    const double sc = (double)r_score[e];
+                    atomicAdd(&usum[rank], sc);      // exact for dyadic scores, hence order-independent (DF_INEXACT_SCORES clear)
+                    atomicAdd(&isum[it], sc);
+                    atomicAdd(&n_u[rank], 1);
+                    present[(size_t)rank_cluster[rank] * table_items + it] = 0;      // table pre-set to -1
+                }
             }
         }
         keys[e] = key;
@@ -160,11 +170,40 @@ __global__ void k_item_prob_isum(const double* __restrict__ isum, int32_t table_
     if (s > 0.0) atomicMin(bmin_bits, (unsigned long long)__double_as_longlong(b > 0.0 ? b : 0.0));
 }
 
+// Shard boundaries on the device (no host round trip): shard r = user ranks [bounds[r], bounds[r+1]) holding ~1/world of
+// the estimated work sum n_u * I_c (lower_bound on the inclusive prefix sum -- integers below 2^53, so every rank gets the
+// same answer), then the rank range [rl, rh) of the clusters this rank touches.  out = bounds[world + 1], rl, rh.
+__global__ void k_shard_bounds(const double* __restrict__ scan, int32_t n_users, int32_t world, int32_t me,
+                               const int32_t* __restrict__ rank_cluster, const int32_t* __restrict__ cstart,
+                               int32_t* __restrict__ out) {
+    const int r = threadIdx.x;
+    if (r <= world) {
+        int32_t b;
+        if (r == 0) b = 0;
+        else if (r >= world) b = n_users;
+        else {
+            const double target = scan[n_users - 1] * (double)r / (double)world;
+            int32_t lo = 0, hi = n_users;
+            while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (scan[mid] < target) lo = mid + 1; else hi = mid; }
+            b = lo;
+        }
+        out[r] = b;
+    }
+    __syncthreads();
+    if (r == 0) {
+        const int32_t ub = out[me], ue = out[me + 1];
+        int32_t rl = 0, rh = 0;
+        if (ue > ub) { rl = cstart[rank_cluster[ub]]; rh = cstart[rank_cluster[ue - 1] + 1]; }
+        out[world + 1] = rl; out[world + 2] = rh;
+    }
+}
+
 // keep the ratings whose user rank lies in [rl, rh) (the clusters this rank touches); warp-aggregated append
 __global__ void k_compact_local(const uint64_t* __restrict__ keys, const float* __restrict__ score, int64_t nnz,
-                                int item_bits, int32_t rl, int32_t rh, uint64_t* __restrict__ keys_out,
+                                int item_bits, const int32_t* __restrict__ rlrh, uint64_t* __restrict__ keys_out,
                                 float* __restrict__ score_out, unsigned long long* __restrict__ counter) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t rl = rlrh[0], rh = rlrh[1];
     bool keep = false;
     uint64_t k = 0;
     if (e < nnz) {
@@ -182,6 +221,22 @@ __global__ void k_compact_local(const uint64_t* __restrict__ keys, const float* 
         keys_out[pos] = k;
         score_out[pos] = score[e];
     }
+}
+
+__global__ void k_init_cbound(unsigned long long* __restrict__ cbound, int32_t n_clusters) {
+    const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_clusters) { cbound[3 * c] = 0ull; cbound[3 * c + 1] = 0ull; cbound[3 * c + 2] = ~0ull; }
+}
+
+// users with at least one emitted item and the log-terms of the scored range: out[0] += users, dout[0] += terms
+__global__ void k_run_totals(const int32_t* __restrict__ out_count, const double* __restrict__ work, int32_t n_rows,
+                             unsigned long long* __restrict__ users, double* __restrict__ terms) {
+    const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    int scored = 0;
+    double t = 0.0;
+    if (r < n_rows) { scored = out_count[r] > 0; t = work[r]; }
+    for (int o = 16; o > 0; o >>= 1) { scored += __shfl_xor_sync(0xffffffffu, scored, o); t += __shfl_xor_sync(0xffffffffu, t, o); }
+    if ((threadIdx.x & 31) == 0) { if (scored) atomicAdd(users, (unsigned long long)scored); atomicAdd(terms, t); }   // integers < 2^53: exact in any order
 }
 
 // sorted keys -> CSR row pointers over user ranks (+ duplicate detection)
@@ -1529,19 +1584,47 @@ __global__ void k_widen_counts(const int32_t* __restrict__ cnt, int32_t n, int64
     if (i < n) out[i] = cnt[i];
 }
 
-// packed output
+// ---------------------------------------------------------------------------------------------
+// Roofline probe: the memory side of k_score_f32 with the arithmetic removed.  CTA = (user, 512-column tile), 128
+// threads, one 16-byte __ldg per thread and row, `rows_per_user` rows per CTA in a per-user pseudo-random order over
+// an [n_rows x ld] 4-byte plane (54 MB panel per tile column at ML-20M shape: L2 resident, like the real kernel).
+// bytes / time of this kernel = what the L2 -> SM path delivers for this access pattern on this box.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCORE_THREADS)
+k_probe_plane_read(const uint32_t* __restrict__ plane, int32_t n_rows, int32_t ld, int32_t rows_per_user,
+                   uint32_t* __restrict__ sink) {
+    const uint32_t* __restrict__ base = plane + (size_t)blockIdx.y * SCOREH_TILE + 4 * threadIdx.x;
+    uint32_t state = 0x9e3779b9u * (blockIdx.x + 1);
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (int32_t k = 0; k < rows_per_user; k += 8) {
+        uint4 h[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            state = state * 1664525u + 1013904223u;
+            const uint32_t row = (uint32_t)(((uint64_t)state * (uint32_t)n_rows) >> 32);
+            h[q] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)row * ld));
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) { acc.x ^= h[q].x; acc.y ^= h[q].y; acc.z ^= h[q].z; acc.w ^= h[q].w; }
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345678u) sink[0] = acc.x;      // keeps the loads alive
+}
+
+// packed output (+ per-row user id / cluster, so that a host can rebuild the triples from the 12-byte (item, score) stream)
 __global__ void k_pack(const int32_t* __restrict__ out_item, const double* __restrict__ out_score,
                        const int32_t* __restrict__ out_count, const int64_t* __restrict__ out_off,
                        int32_t out_stride, int32_t rank_begin, int32_t n_rows,
                        const int32_t* __restrict__ rank_userid, const int32_t* __restrict__ rank_cluster,
                        int32_t* __restrict__ p_user, int32_t* __restrict__ p_item, double* __restrict__ p_s64,
-                       float* __restrict__ p_s32, int32_t* __restrict__ p_cluster) {
+                       float* __restrict__ p_s32, int32_t* __restrict__ p_cluster,
+                       int32_t* __restrict__ row_user, int32_t* __restrict__ row_cluster) {
     const int32_t r = blockIdx.x;
     if (r >= n_rows) return;
     const int32_t n = out_count[r];
     const int64_t off = out_off[r];
     const int32_t rank = rank_begin + r;
     const int32_t uid = rank_userid[rank], c = rank_cluster[rank];
+    if (threadIdx.x == 0) { row_user[r] = uid; row_cluster[r] = c; }
     for (int32_t t = threadIdx.x; t < n; t += blockDim.x) {
         const double s = out_score[(size_t)r * out_stride + t];
         p_user[off + t] = uid;

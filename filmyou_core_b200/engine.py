@@ -27,6 +27,8 @@ EXPORTS = [
     "fy_rm2_set_stream", "fy_rm2_set_ratings", "fy_rm2_set_clustering", "fy_rm2_run", "fy_rm2_max_item",
     "fy_rm2_stats", "fy_rm2_result_count", "fy_rm2_users_scored", "fy_rm2_results", "fy_rm2_results_device", "fy_rm2_score_group",
     "fy_rm2_get_profile", "fy_cooc_counts", "fy_cooc_topk", "fy_knn_neighbours",
+    "fy_rm2_result_row_count", "fy_rm2_result_rows", "fy_rm2_nccl_unique_id", "fy_rm2_comm_init", "fy_rm2_comm_destroy",
+    "fy_rm2_shard_bounds", "fy_rm2_probe_plane_read",
 ]
 # include/filmyou_seqfile.h
 SEQ_EXPORTS = [
@@ -53,7 +55,8 @@ class Rm2Error(RuntimeError):
 class Rm2Params(C.Structure):
     _fields_ = [("lambda_", C.c_double), ("number_of_items", C.c_int32), ("top_n", C.c_int32),
                 ("filter_users", C.c_int32), ("device", C.c_int32), ("shard_rank", C.c_int32),
-                ("shard_count", C.c_int32), ("tie_break", C.c_int32), ("score_mode", C.c_int32)]
+                ("shard_count", C.c_int32), ("tie_break", C.c_int32), ("score_mode", C.c_int32),
+                ("n_gpus", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Rm2Profile(C.Structure):
@@ -62,7 +65,7 @@ class Rm2Profile(C.Structure):
                 ("score_bytes", C.c_double), ("gram_bytes", C.c_double), ("users_scored", C.c_int64),
                 ("kernel_launches", C.c_int64), ("clusters_touched", C.c_int32), ("score_launches", C.c_int32),
                 ("ms_refine", C.c_double), ("bytes_per_term", C.c_double), ("exact_rerun", C.c_int32),
-                ("score_kernel", C.c_int32)]
+                ("score_kernel", C.c_int32), ("ms_gather", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -124,6 +127,14 @@ def load_library():
     L.fy_rm2_score_group.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, i32p, f64p, C.c_int32,
                                      i32p, i32p, f32p, C.c_int64, f64p, C.c_int32]
     L.fy_rm2_get_profile.argtypes = [vp, C.POINTER(Rm2Profile)]
+    L.fy_rm2_result_row_count.argtypes = [vp]
+    L.fy_rm2_result_row_count.restype = C.c_int64
+    L.fy_rm2_result_rows.argtypes = [vp, i32p, i32p, i32p]
+    L.fy_rm2_nccl_unique_id.argtypes = [vp]
+    L.fy_rm2_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
+    L.fy_rm2_comm_destroy.argtypes = [vp]
+    L.fy_rm2_shard_bounds.argtypes = [vp, i32p]
+    L.fy_rm2_probe_plane_read.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, f64p, f64p]
     L.fy_cooc_counts.argtypes = [vp, C.c_int32, C.c_int32, i32p, f64p]
     L.fy_cooc_topk.argtypes = [vp, C.c_int32, i32p, i32p, i32p]
     L.fy_knn_neighbours.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, i32p, i32p, i32p, f64p]
@@ -165,7 +176,7 @@ class Rm2Engine:
     """One context = one GPU.  Thin, 1:1 over the C ABI."""
 
     def __init__(self, lam=0.1, number_of_items=0, top_n=1000, filter_users=0, device=0,
-                 shard_rank=0, shard_count=1, score_mode=0):
+                 shard_rank=0, shard_count=1, score_mode=0, n_gpus=0):
         self._L = load_library()
         self._h = C.c_void_p()
         p = Rm2Params()
@@ -173,6 +184,7 @@ class Rm2Engine:
         p.lambda_, p.number_of_items, p.top_n, p.filter_users = float(lam), int(number_of_items), int(top_n), int(filter_users)
         p.device, p.shard_rank, p.shard_count = int(device), int(shard_rank), int(shard_count)
         p.score_mode = int(score_mode)
+        p.n_gpus = int(n_gpus)
         rc = self._L.fy_rm2_create(C.byref(self._h), C.byref(p))
         if rc != 0:
             self._h = C.c_void_p()
@@ -247,6 +259,63 @@ class Rm2Engine:
                                             _ptr(out["score64"], C.c_double), _ptr(out["score32"], C.c_float),
                                             _ptr(out["cluster"], C.c_int32)))
         return {k: v[:n] for k, v in out.items()}
+
+    def result_rows(self):
+        """(user, cluster, count) per scored row, rows in the order of the packed triples."""
+        n = int(self._L.fy_rm2_result_row_count(self._h))
+        if n < 0:
+            raise Rm2Error(-8, "no results")
+        u, c, k = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.int32)
+        self._check(self._L.fy_rm2_result_rows(self._h, _ptr(u, C.c_int32), _ptr(c, C.c_int32), _ptr(k, C.c_int32)))
+        return u, c, k
+
+    def results_compact(self, out=None):
+        """The 12-byte-per-triple read-back: dict(item, score64, row_user, row_cluster, row_count); `out` may hold
+        preallocated (pinned) item / score64 arrays.  expand_compact() rebuilds the five packed arrays."""
+        n = self.result_count()
+        if n < 0:
+            raise Rm2Error(-8, "no results")
+        if out is None:
+            out = dict(item=np.empty(n, np.int32), score64=np.empty(n, np.float64))
+        self._check(self._L.fy_rm2_results(self._h, None, _ptr(out["item"], C.c_int32), _ptr(out["score64"], C.c_double), None, None))
+        u, c, k = self.result_rows()
+        return dict(item=out["item"][:n], score64=out["score64"][:n], row_user=u, row_cluster=c, row_count=k)
+
+    @staticmethod
+    def expand_compact(r):
+        """(item, score64, rows) -> the packed triples fy_rm2_results returns (user, item, score64, score32, cluster)."""
+        return dict(user=np.repeat(r["row_user"], r["row_count"]), item=r["item"], score64=r["score64"],
+                    score32=r["score64"].astype(np.float32), cluster=np.repeat(r["row_cluster"], r["row_count"]))
+
+    @staticmethod
+    def nccl_unique_id():
+        """128 bytes from ncclGetUniqueId (rank 0 calls this and hands the bytes to every rank)."""
+        buf = (C.c_ubyte * 128)()
+        rc = load_library().fy_rm2_nccl_unique_id(C.cast(buf, C.c_void_p))
+        if rc != 0:
+            raise Rm2Error(rc, "fy_rm2_nccl_unique_id failed (is libnccl.so.2 loadable?)")
+        return bytes(buf)
+
+    def comm_init(self, unique_id, world, rank):
+        """Attach an NCCL communicator: fy_rm2_run then ends with the in-library exchange of the top-N blocks and
+        results() on every rank holds the whole job."""
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self._L.fy_rm2_comm_init(self._h, C.cast(buf, C.c_void_p), int(world), int(rank)))
+
+    def comm_destroy(self):
+        self._check(self._L.fy_rm2_comm_destroy(self._h))
+
+    def shard_bounds(self):
+        b = np.zeros(int(self.params.shard_count if self.params.n_gpus <= 1 else self.params.n_gpus) + 1, np.int32)
+        self._check(self._L.fy_rm2_shard_bounds(self._h, _ptr(b, C.c_int32)))
+        return b
+
+    def probe_plane_read(self, n_rows, n_users, rows_per_user, reps=5):
+        """(GB/s, ms per launch) of the score kernel's access pattern without its arithmetic (roofline probe)."""
+        g, ms = C.c_double(0), C.c_double(0)
+        self._check(self._L.fy_rm2_probe_plane_read(self._h, int(n_rows), int(n_users), int(rows_per_user), int(reps),
+                                                     C.byref(g), C.byref(ms)))
+        return g.value, ms.value
 
     def results_device(self):
         """field -> object exposing __cuda_array_interface__ over the device-resident packed arrays

@@ -28,7 +28,11 @@
  *     Nothing throws or aborts across the boundary (the reference's only convention is
  *     "throw RuntimeException => task fails", M/rm/RM2Job.java:265-268).
  *   - The caller owns every buffer it passes; inputs are copied during the call, never retained.
- *   - A context is single-caller; distinct contexts are independent.  One context drives one GPU.
+ *   - A context is single-caller; distinct contexts are independent.  One context drives one GPU, or
+ *     fy_rm2_params.n_gpus of them from one process.
+ *   - Capacity: one cluster needs 24 * I_c * ld bytes of device memory for its H planes (I_c = items rated in the
+ *     cluster, ld = I_c rounded up to 512): 17 GB at ML-20M shape, ~86 GB at I_c = 60 000; beyond what the device
+ *     holds fy_rm2_run fails with FY_E_NOMEM.
  *   - There is NO CPU fallback: without a usable CUDA device fy_rm2_create fails with FY_E_CUDA.
  *
  * Ordering contract: the reference leaves the order among equal scores to
@@ -45,7 +49,7 @@
 extern "C" {
 #endif
 
-#define FY_RM2_ABI_VERSION 2
+#define FY_RM2_ABI_VERSION 3
 
 typedef enum fy_status {
     FY_OK = 0,
@@ -76,6 +80,14 @@ typedef struct fy_rm2_params {
     int32_t score_mode;        /* 0 = auto: stream the 4-byte hi-word plane of H, then re-score the */
                                /*     provably sufficient candidate set exactly in fp64;            */
                                /* 1 = exact: stream the fp64 plane for every term                   */
+    int32_t n_gpus;            /* 0/1 = this context drives `device` only.  n > 1 = ONE context drives */
+                               /*     devices device .. device+n-1 from one host process: the users are */
+                               /*     sharded over them exactly as shard_rank/shard_count would (which  */
+                               /*     must then be 0/1), inputs are uploaded to every device, results   */
+                               /*     come back concatenated in shard order.  The GPU analogue of       */
+                               /*     numReduceTasks = numberOfClusters (M/rm/RM2Job.java:251) and of    */
+                               /*     the cluster-split fan-out (M/common/AbstractByClusterAndCountMapper.java:86-102) */
+    int32_t reserved;          /* must be 0                                                         */
 } fy_rm2_params;
 
 typedef struct fy_rm2_ctx fy_rm2_ctx;
@@ -117,10 +129,31 @@ int64_t fy_rm2_users_scored(const fy_rm2_ctx* ctx);
 int fy_rm2_results(fy_rm2_ctx* ctx, int32_t* user, int32_t* item, double* score64, float* score32,
                    int32_t* cluster);
 
+/* The same results as a 12-byte-per-triple stream: fy_rm2_results(ctx, NULL, item, score64, NULL, NULL) plus one
+ * (user, cluster, count) record per scored row, rows in the order of the triples.  user/cluster/score32 of a triple
+ * follow from its row and (float) score64, so a host reads 12 B instead of 24 B per triple.  Any pointer may be NULL. */
+int64_t fy_rm2_result_row_count(const fy_rm2_ctx* ctx);
+int fy_rm2_result_rows(fy_rm2_ctx* ctx, int32_t* user, int32_t* cluster, int32_t* count);
+
 /* Device-resident view of the same packed arrays (valid until the next run / destroy), so that a
  * multi-GPU host can hand them to NCCL without a host round trip.  Any output pointer may be NULL. */
 int fy_rm2_results_device(fy_rm2_ctx* ctx, const int32_t** user, const int32_t** item, const double** score64,
                           const float** score32, const int32_t** cluster);
+
+/* ---- one process per GPU (torchrun / MPI style): the exchange step of the job, inside the library -----------------
+ * Rank 0 obtains an id with fy_rm2_nccl_unique_id and hands the bytes to the other ranks by any means; every rank then
+ * calls fy_rm2_comm_init on its context (created with shard_rank = rank, shard_count = world).  From then on fy_rm2_run
+ * ends with ONE grouped NCCL exchange of the dense top-N blocks over NVLink, issued on the run's stream, and
+ * fy_rm2_results / result_count / result_rows on EVERY rank describe the whole job (all users, in (cluster, user id)
+ * order); fy_rm2_users_scored stays this rank's share.  This replaces the shuffle + per-reducer part files of RM2-3
+ * (M/rm/RM2Job.java:214-270).  libnccl.so.2 is resolved at run time (dlopen), so a process that never calls these
+ * two functions does not need NCCL.  fy_rm2_comm_destroy detaches (also done by fy_rm2_destroy). */
+#define FY_NCCL_UNIQUE_ID_BYTES 128
+int fy_rm2_nccl_unique_id(void* id_out /* FY_NCCL_UNIQUE_ID_BYTES */);
+int fy_rm2_comm_init(fy_rm2_ctx* ctx, const void* id /* FY_NCCL_UNIQUE_ID_BYTES */, int32_t world, int32_t rank);
+int fy_rm2_comm_destroy(fy_rm2_ctx* ctx);
+/* user-rank boundaries of the shards of the last run: bounds[shard_count + 1] */
+int fy_rm2_shard_bounds(const fy_rm2_ctx* ctx, int32_t* bounds);
 
 /* Fine seam: one reduce() group, exactly the records the reducer receives
  * (M/rm/AbstractRM2Reducer.java:149-174): n_group_users (user, userSum) records, then the group's
@@ -150,8 +183,15 @@ typedef struct fy_rm2_profile {
     double bytes_per_term;  /* 4 (hi-word plane) or 8 (fp64 plane): what score_bytes counts      */
     int32_t exact_rerun;    /* 1 if a candidate list overflowed and the run was redone in exact mode */
     int32_t score_kernel;   /* dominant kernel of the last run: 0 = k_score (fp64), 1 = k_score_hi, 2 = k_score_f32 */
+    double ms_gather;       /* the NCCL exchange of the top-N blocks (0 without a communicator)      */
 } fy_rm2_profile;
 int fy_rm2_get_profile(const fy_rm2_ctx* ctx, fy_rm2_profile* out);
+
+/* Roofline probe for the bench: the memory side of the dominant score kernel with the arithmetic removed (same grid,
+ * same 16-byte loads, `rows_per_user` pseudo-random rows of an [n_rows x ld] 4-byte plane per (user, 512-column tile)
+ * CTA).  Returns the GB/s the L2 -> SM path of THIS box delivers for that access pattern. */
+int fy_rm2_probe_plane_read(fy_rm2_ctx* ctx, int32_t n_rows, int32_t n_users, int32_t rows_per_user, int32_t reps,
+                            double* gb_per_s, double* ms_per_launch);
 
 /* ---- Config 3: item-item co-occurrence counts on the binarised ratings -------
  * Replaces the Mahout RowSimilarityJob(CooccurrenceCountSimilarity) call at

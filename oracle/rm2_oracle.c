@@ -335,63 +335,96 @@ int orc_rm2_run(const orc_params* p,
         const double log_K = log((double)K);              /* :329 */
         const double t_begin = now_s();
         int oom = 0;
-        int64_t n_slots_used = 0;
-        for (int64_t v = 0; v < K; v++) n_slots_used += (slot[v] >= 0);
-        /* Users are independent (one reduce task scores them one after the other); with fewer wanted users
-         * than threads the candidates of a user are spread over the threads instead, so that every host
-         * core is busy.  The arithmetic per (user, candidate) is the same either way. */
-        const int inner_par = (n_slots_used < (int64_t)threads);
-#pragma omp parallel for schedule(dynamic, 1) if (!inner_par)
-        for (int64_t u = 0; u < K; u++) {
+        /* Users are independent (one reduce task scores them one after the other, :202-226).  To keep every host
+         * thread busy whatever the mix of light and heavy users, the (user, block of 64 candidates) pairs are the
+         * parallel tasks; the arithmetic of one (user, candidate) pair -- the loops :337-348 -- is untouched.
+         * cand_stride > 1 (timing only, bench.py) scores every stride-th candidate of a user: the cost of a
+         * candidate does not depend on which one it is, so time * stride extrapolates to the whole user. */
+        const int64_t stride = p->cand_stride > 1 ? p->cand_stride : 1;
+        typedef struct { cand_t* prefs; int32_t* rj; int32_t* cand_i; int64_t np; int64_t task0; int n; } ujob_t;
+        ujob_t* job = (ujob_t*)calloc((size_t)K, sizeof(ujob_t));
+        int64_t n_tasks = 0;
+        const int64_t CH = 64;
+        if (!job) { oom = 1; }
+        for (int64_t u = 0; u < K && !oom; u++) {
             if (slot[u] < 0) continue;
             const int64_t r0 = rowptr[u0 + u], r1 = rowptr[u0 + u + 1];
             const int n = (int)(r1 - r0);
             const int64_t cu = I - n;
-            cand_t* prefs = (cand_t*)malloc(sizeof(cand_t) * (size_t)cu);
             char* rated = (char*)calloc((size_t)I, 1);
-            int32_t* rj = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
-            int32_t* cand_i = (int32_t*)malloc(sizeof(int32_t) * (size_t)(cu > 0 ? cu : 1));
-            if (!prefs || !rated || !rj || !cand_i) { oom = 1; free(prefs); free(rated); free(rj); free(cand_i); continue; }
-            for (int k = 0; k < n; k++) { rj[k] = loc[rt[r0 + k].item]; rated[rj[k]] = 1; }
-            const double pvpi = (n - 1) * log_items - n * log_K;               /* :328-329 */
-            int64_t np = 0;
-            for (int64_t i = 0; i < I; i++) if (!rated[i]) cand_i[np++] = (int32_t)i;   /* unratedItems :206-208 */
-#pragma omp parallel for schedule(dynamic, 8) if (inner_par)
-            for (int64_t q = 0; q < np; q++) {                                  /* :332 */
-                const int64_t i = cand_i[q];
-                double logResult = 0.0;                                        /* :334 */
-                for (int k = 0; k < n; k++) {                                   /* :337 */
-                    const int64_t j = rj[k];
-                    double sum = 0.0;                                          /* :339 */
-                    if (p->mode == ORC_MODE_GRAM) {
-                        sum = G[(size_t)i * (size_t)I + (size_t)j] - PAT(u, i) * PAT(u, j);
-                    } else if (transposed) {
-                        const double* a = P + (size_t)i * (size_t)K;
-                        const double* b = P + (size_t)j * (size_t)K;
-                        for (int64_t v = 0; v < u; v++) sum += a[v] * b[v];
-                        for (int64_t v = u + 1; v < K; v++) sum += a[v] * b[v];
-                    } else {
-                        for (int64_t v = 0; v < K; v++) {                      /* :342-346 */
-                            if (v == u) continue;                              /* neighbours.remove(userID) :216 */
-                            sum += P[(size_t)v * (size_t)I + (size_t)i] * P[(size_t)v * (size_t)I + (size_t)j];
-                        }
-                    }
-                    logResult += log(sum);                                     /* :348 */
-                }
-                logResult += pvpi;                                             /* :352 */
-                prefs[q].score = logResult;
-                prefs[q].item = items[i];
-            }
-            qsort(prefs, (size_t)np, sizeof(cand_t), cmp_cand);
-            const int64_t iterations = np < p->top_n ? np : p->top_n;          /* :360 */
-            for (int64_t k = 0; k < iterations; k++) {                         /* :361-369 */
-                res->user[slot[u] + k] = us[u0 + u].id;
-                res->item[slot[u] + k] = prefs[k].item;
-                res->score[slot[u] + k] = prefs[k].score;
-                res->cluster[slot[u] + k] = c;
-            }
-            free(prefs); free(rated); free(rj); free(cand_i);
+            job[u].n = n;
+            job[u].rj = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+            job[u].cand_i = (int32_t*)malloc(sizeof(int32_t) * (size_t)(cu > 0 ? cu : 1));
+            job[u].prefs = (cand_t*)malloc(sizeof(cand_t) * (size_t)(cu > 0 ? cu : 1));
+            if (!rated || !job[u].rj || !job[u].cand_i || !job[u].prefs) { oom = 1; free(rated); break; }
+            for (int k = 0; k < n; k++) { job[u].rj[k] = loc[rt[r0 + k].item]; rated[job[u].rj[k]] = 1; }
+            int64_t np = 0, seen = 0;
+            for (int64_t i = 0; i < I; i++)                                     /* unratedItems :206-208 */
+                if (!rated[i]) { if (seen % stride == 0) job[u].cand_i[np++] = (int32_t)i; seen++; }
+            job[u].np = np;
+            job[u].task0 = n_tasks;
+            n_tasks += (np + CH - 1) / CH;
+            free(rated);
         }
+        int64_t* task_user = NULL;
+        if (!oom) {
+            task_user = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_tasks > 0 ? n_tasks : 1));
+            if (!task_user) oom = 1;
+            else for (int64_t u = 0; u < K; u++)
+                if (slot[u] >= 0) for (int64_t t = job[u].task0, e = job[u].task0 + (job[u].np + CH - 1) / CH; t < e; t++) task_user[t] = u;
+        }
+        if (!oom) {
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int64_t t = 0; t < n_tasks; t++) {
+                const int64_t u = task_user[t];
+                const ujob_t* jb = &job[u];
+                const int n = jb->n;
+                const int32_t* rj = jb->rj;
+                const double pvpi = (n - 1) * log_items - n * log_K;           /* :328-329 */
+                const int64_t q0 = (t - jb->task0) * CH, q1 = q0 + CH < jb->np ? q0 + CH : jb->np;
+                for (int64_t q = q0; q < q1; q++) {                             /* :332 */
+                    const int64_t i = jb->cand_i[q];
+                    double logResult = 0.0;                                    /* :334 */
+                    for (int k = 0; k < n; k++) {                               /* :337 */
+                        const int64_t j = rj[k];
+                        double sum = 0.0;                                      /* :339 */
+                        if (p->mode == ORC_MODE_GRAM) {
+                            sum = G[(size_t)i * (size_t)I + (size_t)j] - PAT(u, i) * PAT(u, j);
+                        } else if (transposed) {
+                            const double* a = P + (size_t)i * (size_t)K;
+                            const double* b = P + (size_t)j * (size_t)K;
+                            for (int64_t v = 0; v < u; v++) sum += a[v] * b[v];
+                            for (int64_t v = u + 1; v < K; v++) sum += a[v] * b[v];
+                        } else {
+                            for (int64_t v = 0; v < K; v++) {                  /* :342-346 */
+                                if (v == u) continue;                          /* neighbours.remove(userID) :216 */
+                                sum += P[(size_t)v * (size_t)I + (size_t)i] * P[(size_t)v * (size_t)I + (size_t)j];
+                            }
+                        }
+                        logResult += log(sum);                                 /* :348 */
+                    }
+                    logResult += pvpi;                                         /* :352 */
+                    jb->prefs[q].score = logResult;
+                    jb->prefs[q].item = items[i];
+                }
+            }
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int64_t u = 0; u < K; u++) {
+                if (slot[u] < 0) continue;
+                qsort(job[u].prefs, (size_t)job[u].np, sizeof(cand_t), cmp_cand);  /* PriorityQueue poll order :358-369 */
+                int64_t iterations = job[u].np < p->top_n ? job[u].np : p->top_n;  /* :360 */
+                const int64_t room = (I - job[u].n) < p->top_n ? (I - job[u].n) : p->top_n;
+                for (int64_t k = 0; k < room; k++) {                            /* :361-369 */
+                    const int64_t kk = k < iterations ? k : iterations - 1;     /* stride > 1: pad (timing mode only) */
+                    res->user[slot[u] + k] = us[u0 + u].id;
+                    res->item[slot[u] + k] = job[u].prefs[kk].item;
+                    res->score[slot[u] + k] = job[u].prefs[kk].score;
+                    res->cluster[slot[u] + k] = c;
+                }
+            }
+        }
+        if (job) for (int64_t u = 0; u < K; u++) { free(job[u].prefs); free(job[u].rj); free(job[u].cand_i); }
+        free(job); free(task_user);
         res->seconds += now_s() - t_begin;
         for (int64_t v = 0; v < K; v++) if (slot[v] >= 0) res->users_scored++;
         res->count += nslots;

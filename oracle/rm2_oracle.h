@@ -60,7 +60,9 @@ typedef struct {
     int32_t top_n;           /* RMRecommenderDriver.numberOfRecommendations :110            */
     int32_t filter_users;    /* RMRecommenderDriver.filterUsers :197,220-223                */
     int32_t mode;            /* ORC_MODE_*                                                  */
-    int32_t threads;         /* OpenMP threads over users (1 = what one reduce task does)   */
+    int32_t threads;         /* OpenMP threads (1 = what one reduce task does)              */
+    int32_t cand_stride;     /* 0/1 = every candidate; s > 1 = every s-th candidate of a user (TIMING ONLY:  */
+                             /* bench.py's bounded CPU sample; time * s extrapolates to the whole user)       */
 } orc_params;
 
 typedef struct orc_result orc_result;

@@ -28,7 +28,7 @@ class OracleError(RuntimeError):
 
 class _Params(C.Structure):
     _fields_ = [("lambda_", C.c_double), ("number_of_items", C.c_int32), ("top_n", C.c_int32),
-                ("filter_users", C.c_int32), ("mode", C.c_int32), ("threads", C.c_int32)]
+                ("filter_users", C.c_int32), ("mode", C.c_int32), ("threads", C.c_int32), ("cand_stride", C.c_int32)]
 
 
 def build(force=False):
@@ -91,14 +91,14 @@ def stats(r_user, r_item, r_score, users):
 
 
 def run(r_user, r_item, r_score, cl_user, cl_cluster, cluster_size, lam, number_of_items, top_n,
-        filter_users=0, mode=MODE_LITERAL_FAST, threads=0, only_users=None):
+        filter_users=0, mode=MODE_LITERAL_FAST, threads=0, only_users=None, cand_stride=1):
     """Whole RM2 job on the CPU.  Returns dict(user, item, score64, score32, cluster, seconds, users_scored)."""
     r_user, r_item = _i32(r_user), _i32(r_item)
     r_score = np.ascontiguousarray(r_score, dtype=np.float32)
     cl_user, cl_cluster, cluster_size = _i32(cl_user), _i32(cl_cluster), _i32(cluster_size)
     if threads <= 0:
         threads = os.cpu_count() or 1
-    prm = _Params(float(lam), int(number_of_items), int(top_n), int(filter_users), int(mode), int(threads))
+    prm = _Params(float(lam), int(number_of_items), int(top_n), int(filter_users), int(mode), int(threads), int(cand_stride))
     only = _i32(only_users) if only_users is not None and len(only_users) else np.zeros(0, np.int32)
     h = C.c_void_p()
     rc = lib().orc_rm2_run(C.byref(prm), _p(r_user, C.c_int32), _p(r_item, C.c_int32), _p(r_score, C.c_float),

@@ -74,3 +74,31 @@ def assert_parity(got, want, rel=1e-6, what=""):
             worst = max(worst, float(r))
     assert worst <= rel, "%s: worst relative score error %.3g > %.1g" % (what, worst, rel)
     return worst
+
+
+def assert_parity_near_ties(got, want, rel=1e-6, tie_rel=1e-12, what=""):
+    """Like assert_parity, for comparisons at full scale: the top-N ids must be the oracle's, in the oracle's order, EXCEPT
+    that two items whose ORACLE scores differ by less than tie_rel relative may swap places (or straddle the N-th place):
+    the engine and the oracle both round in the 1e-13 range, so such a pair has no defined order (the reference's own
+    PriorityQueue leaves even exact ties unordered, M/util/IntDouble.java:31-34).  Returns (worst relative score error,
+    number of users with such a swap)."""
+    g, w = by_user(got), by_user(want)
+    assert set(g) == set(w), "%s: scored user sets differ: %d vs %d" % (what, len(g), len(w))
+    worst, swapped = 0.0, 0
+    for u in w:
+        gi, gs = g[u]
+        wi, ws = w[u]
+        assert len(gi) == len(wi), "%s: user %d emits %d items, oracle %d" % (what, u, len(gi), len(wi))
+        r = np.max(np.abs(gs - ws) / np.maximum(np.abs(ws), 1e-300))     # position-wise: scores are sorted on both sides
+        worst = max(worst, float(r))
+        if np.array_equal(gi, wi):
+            continue
+        swapped += 1
+        pos = {int(i): k for k, i in enumerate(wi)}
+        for k in np.flatnonzero(gi != wi):
+            k2 = pos.get(int(gi[k]))
+            ref = ws[k2] if k2 is not None else ws[-1]                   # not in the oracle's list: must tie with its N-th place
+            assert abs(ref - ws[k]) <= tie_rel * abs(ws[k]), \
+                "%s: user %d position %d: item %d vs oracle %d is not a near-tie (oracle scores %.17g / %.17g)" % (what, u, k, gi[k], wi[k], ref, ws[k])
+    assert worst <= rel, "%s: worst relative score error %.3g > %.1g" % (what, worst, rel)
+    return worst, swapped

@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     L = fy.load_library()
     for name in _declared() + _declared("filmyou_seqfile.h") + _declared("filmyou_nmf.h"):
         assert hasattr(L, name), name
-    assert L.fy_rm2_abi_version() == 2
+    assert L.fy_rm2_abi_version() == 3
 
 
 def test_default_params_match_the_reference_defaults():

@@ -9,7 +9,7 @@ import filmyou_core_b200 as fy
 from filmyou_core_b200 import datagen
 from oracle import rm2_oracle as orc
 
-from conftest import assert_parity, by_user
+from conftest import assert_parity, assert_parity_near_ties, by_user
 
 pytestmark = pytest.mark.gpu
 REL = 1e-6          # north_star: "scores within 1e-6 relative in the log domain against Java doubles"
@@ -111,25 +111,52 @@ def test_candidate_overflow_falls_back_to_the_exact_stream():
     assert_parity(a, cpu_run(r, 0.1, 605, 5), REL, "overflow")
 
 
-def test_ml20m_sampled_users_vs_oracle():
-    # BASELINE.json headline shape (138 493 x 26 744, 20 M half-star ratings, 50 clusters): the whole job on
-    # the GPU, the literal CPU loop (2*K*n_u*c_u flops per user) on a seeded sample of light and medium users
+def _subset(got, users):
+    g = by_user(got)
+    return {k: np.concatenate([np.full(len(g[int(u)][0]), int(u)) if k == "user" else
+                               (g[int(u)][0] if k == "item" else g[int(u)][1]) for u in users])
+            for k in ("user", "item", "score64")}
+
+
+def _full_cluster_and_heaviest(r, got, what, n_heavy):
+    """Parity where the numbers are quoted: EVERY user of the cluster that holds the most active user of the workload
+    against the oracle's GRAM mode (G - self algebra in fp64, ~1e12 multiply-adds: the literal loop would be ~1e14), and
+    the n_heavy most active users of the whole workload against MODE_LITERAL_FAST (the reducer's own loop nest and order).
+    These are the users where the candidate margin (eps_u = n_u * 2.5e-7), the candidate cap, the fp32 exponent-peel range
+    and the most-active-first processing order matter."""
+    n_u = np.bincount(r.user, minlength=r.n_users + 1)
+    order = r.cl_user[np.argsort(-n_u[r.cl_user], kind="stable")]
+    heavy = order[:n_heavy].astype(np.int32)
+    cl_of = np.zeros(r.n_users + 1, np.int64); cl_of[r.cl_user] = r.cl_cluster
+    c = int(cl_of[heavy[0]])
+    members = r.cl_user[r.cl_cluster == c].astype(np.int32)
+    want = cpu_run(r, 0.1, r.n_items, 100, only_users=members, mode=orc.MODE_GRAM)
+    assert want["users_scored"] == len(members)
+    worst, swapped = assert_parity_near_ties(_subset(got, list(by_user(want))), want, REL, 1e-12, what + " cluster %d (GRAM)" % c)
+    assert worst < 1e-9 and swapped <= max(2, len(members) // 200), (worst, swapped)
+    want = cpu_run(r, 0.1, r.n_items, 100, only_users=heavy, mode=orc.MODE_LITERAL_FAST)
+    worst_h, swapped_h = assert_parity_near_ties(_subset(got, list(by_user(want))), want, REL, 1e-12, what + " heaviest users (literal)")
+    assert worst_h < 1e-9
+    return {"cluster": c, "cluster_users": int(len(members)), "max_n_u": int(n_u[heavy[0]]), "worst_rel": max(worst, worst_h),
+            "near_tie_swaps": swapped + swapped_h}
+
+
+def test_ml20m_full_cluster_and_heaviest_users_vs_oracle():
+    # BASELINE.json headline shape (138 493 x 26 744, 20 M half-star ratings, 50 clusters), the whole job on the GPU
     r = datagen.generate("ml-20m")
     got = gpu_run(r, 0.1, r.n_items, 100)
     assert got["users_scored"] == r.n_users and len(got["user"]) == r.n_users * 100
     assert got["profile"]["exact_rerun"] == 0
+    info = _full_cluster_and_heaviest(r, got, "ml-20m", 4)
+    assert info["cluster_users"] > 2000 and info["max_n_u"] > 5000
+    print("ml-20m parity:", info)
+    # light and medium users spread over other clusters, the reducer's literal loop
     n_u = np.bincount(r.user, minlength=r.n_users + 1)
     rng = np.random.default_rng(20)
     light = rng.choice(np.flatnonzero((n_u >= 20) & (n_u <= 30)), size=6, replace=False)
     medium = rng.choice(np.flatnonzero((n_u >= 100) & (n_u <= 140)), size=2, replace=False)
-    sample = np.concatenate([light, medium]).astype(np.int32)
-    want = cpu_run(r, 0.1, r.n_items, 100, only_users=sample)
-    g = by_user(got)
-    sub = {k: np.concatenate([np.full(len(g[int(u)][0]), int(u)) if k == "user" else
-                              (g[int(u)][0] if k == "item" else g[int(u)][1])
-                              for u in by_user(want)]) for k in ("user", "item", "score64")}
-    worst = assert_parity(sub, want, REL, "ml-20m sample")
-    assert worst < 1e-9
+    want = cpu_run(r, 0.1, r.n_items, 100, only_users=np.concatenate([light, medium]).astype(np.int32))
+    assert assert_parity(_subset(got, list(by_user(want))), want, REL, "ml-20m sample") < 1e-9
     # size-independent properties over ALL users
     items = got["item"].reshape(r.n_users, 100); scores = got["score64"].reshape(r.n_users, 100)
     assert np.all(np.diff(scores, axis=1) <= 0)
@@ -139,21 +166,14 @@ def test_ml20m_sampled_users_vs_oracle():
     assert tot == otot and np.array_equal(us, ous) and np.array_equal(ip, oip[:len(ip)])
 
 
-def test_netflix_shape_sampled_users_and_properties():
-    # BASELINE.json configs[4] shape (480 189 x 17 770, 100 M ratings, 50 clusters) on ONE GPU: the whole job, the
-    # literal CPU loop on a seeded sample of light users, and the size-independent properties over all users
+def test_netflix_shape_full_cluster_and_properties():
+    # BASELINE.json configs[4] shape (480 189 x 17 770, 100 M ratings, 50 clusters) on ONE GPU: the whole job; every user of
+    # one full cluster (~9 600 users) and the heaviest users against the oracle; size-independent properties over all users
     r = datagen.generate("netflix")
     got = gpu_run(r, 0.1, r.n_items, 100)
     assert got["users_scored"] == r.n_users and len(got["user"]) == r.n_users * 100
-    n_u = np.bincount(r.user, minlength=r.n_users + 1)
-    rng = np.random.default_rng(40)
-    sample = rng.choice(np.flatnonzero((n_u >= 20) & (n_u <= 24)), size=4, replace=False).astype(np.int32)
-    want = cpu_run(r, 0.1, r.n_items, 100, only_users=sample)
-    g = by_user(got)
-    sub = {k: np.concatenate([np.full(len(g[int(u)][0]), int(u)) if k == "user" else
-                              (g[int(u)][0] if k == "item" else g[int(u)][1])
-                              for u in by_user(want)]) for k in ("user", "item", "score64")}
-    assert assert_parity(sub, want, REL, "netflix sample") < 1e-9
+    info = _full_cluster_and_heaviest(r, got, "netflix", 2)
+    print("netflix parity:", info)
     items = got["item"].reshape(r.n_users, 100); scores = got["score64"].reshape(r.n_users, 100)
     assert np.all(np.diff(scores, axis=1) <= 0)
     srt = np.sort(items, axis=1)
@@ -165,6 +185,63 @@ def test_netflix_shape_sampled_users_and_properties():
     us, ip, tot = got["stats"]
     ous, _, oip, otot = orc.stats(r.user, r.item, r.score, r.cl_user)
     assert tot == otot and np.array_equal(us, ous) and np.array_equal(ip, oip[:len(ip)])
+
+
+def test_compact_result_stream_rebuilds_the_packed_triples():
+    # the 12-byte read-back (item, score64) + one (user, cluster, count) record per row = the five packed arrays
+    r = datagen.generate("small")
+    with fy.Rm2Engine(lam=0.1, number_of_items=r.n_items, top_n=600) as eng:       # N > items: ragged row counts
+        eng.set_ratings(r.user, r.item, r.score)
+        eng.set_clustering(r.cl_user, r.cl_cluster, r.cluster_size)
+        eng.run()
+        full = eng.results()
+        comp = eng.results_compact()
+        rebuilt = fy.Rm2Engine.expand_compact(comp)
+    assert len(set(comp["row_count"].tolist())) > 1
+    for k in ("user", "item", "score64", "score32", "cluster"):
+        assert np.array_equal(full[k], rebuilt[k]), k
+
+
+def test_n_gpus_context_equals_one_gpu():
+    # fy_rm2_params.n_gpus: ONE context, one host process, several devices -- the result a JVM host gets from one native call
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = datagen.generate("ml-100k")
+    ref = gpu_run(r, 0.1, r.n_items, 100)
+    n = min(4, torch.cuda.device_count())
+    got = gpu_run(r, 0.1, r.n_items, 100, n_gpus=n)
+    for k in ("user", "item", "score64", "score32", "cluster"):
+        assert np.array_equal(ref[k], got[k]), k
+    assert got["users_scored"] == ref["users_scored"]
+    assert got["stats"][2] == ref["stats"][2] and np.array_equal(got["stats"][0], ref["stats"][0])
+    with fy.Rm2Engine(lam=0.1, number_of_items=r.n_items, top_n=100, n_gpus=n) as eng:
+        eng.set_ratings(r.user, r.item, r.score)
+        eng.set_clustering(r.cl_user, r.cl_cluster, r.cluster_size)
+        eng.run()
+        rebuilt = fy.Rm2Engine.expand_compact(eng.results_compact())
+    assert all(np.array_equal(ref[k], rebuilt[k]) for k in ("user", "item", "score64", "cluster"))
+
+
+def test_multi_process_exchange_digest_equals_one_gpu(tmp_path):
+    # one process per GPU, the NCCL exchange inside the library (fy_rm2_comm_init): rank 0's digest of the whole job's
+    # (user, item, score64 bits) must equal the 1-GPU digest -- the check SCALE relies on
+    import json, os, subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    def bench(n):
+        cmd = [sys.executable, os.path.join(root, "bench.py")] if n == 1 else \
+              [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+               "--master-port", "29653", os.path.join(root, "bench.py")]
+        out = subprocess.check_output(cmd + ["--gpus", str(n), "--steps", "1", "--warmup", "3", "--workload", "ml-1m",
+                                             "--no-cpu-baseline", "--no-secondary"], text=True, cwd=root)
+        return json.loads(out.strip().splitlines()[-1])
+    one, two = bench(1), bench(2)
+    assert one["result_digest"]["triples"] == 6040 * 100
+    assert two["result_digest"] == one["result_digest"]
+    assert two["n_gpus"] == 2 and two["users_scored"] == one["users_scored"] == 6040
+    assert two["e2e"]["d2h_bytes_per_step"] == one["e2e"]["d2h_bytes_per_step"]
 
 
 def test_more_than_4096_recommendations_per_user():
