@@ -1129,6 +1129,32 @@ __device__ __forceinline__ void peel_exponent_f(float& p, int& ex) {
     p = __int_as_float((b & 0x007fffff) | 0x3f800000);
 }
 
+// sm_100 packed fp32: one FFMA2 / FMUL2 does two candidates (each lane rounds exactly like the scalar FFMA / FMUL), which
+// halves the arithmetic issue slots of a kernel that the plane-read probe shows to be issue bound, not L2 bound
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack_f32x2(float lo, float hi) {
+    return ((f32x2_t)__float_as_uint(hi) << 32) | (f32x2_t)__float_as_uint(lo);
+}
+__device__ __forceinline__ f32x2_t pack_u32x2(uint32_t lo, uint32_t hi) { return ((f32x2_t)hi << 32) | (f32x2_t)lo; }
+__device__ __forceinline__ f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2_t fmul2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ void peel_exponent_f2(f32x2_t& p, int& e0, int& e1) {
+    uint32_t lo = (uint32_t)p, hi = (uint32_t)(p >> 32);
+    e0 += (int)(lo >> 23) - 127;                        // p > 0: no sign bit
+    e1 += (int)(hi >> 23) - 127;
+    lo = (lo & 0x007fffffu) | 0x3f800000u;
+    hi = (hi & 0x007fffffu) | 0x3f800000u;
+    p = pack_u32x2(lo, hi);
+}
+
 template <int LF>
 __global__ void __launch_bounds__(SCORE_THREADS)
 k_score_f32(const uint32_t* __restrict__ Hf, int32_t I_c, int32_t ld, int32_t rank_begin, int32_t slot0,
@@ -1136,8 +1162,7 @@ k_score_f32(const uint32_t* __restrict__ Hf, int32_t I_c, int32_t ld, int32_t ra
             const double* __restrict__ csr_c, const double* __restrict__ c_b, double plane_scale, int32_t scale_exp,
             double log_items, double log_K, double* __restrict__ scores, unsigned long long* __restrict__ ustat,
             const int32_t* __restrict__ perm /* users of the batch, most active first (null = rank order) */) {
-    __shared__ int32_t s_j[SCORE_CHUNK];
-    __shared__ float s_c[SCORE_CHUNK];
+    __shared__ uint2 s_jc[SCORE_CHUNK];                  // (local row j, float bits of c(u,j)): one 8-byte load per row
     __shared__ unsigned s_rated[SCOREH_TILE / 32];
 
     // longest-processing-time-first: the CTA of a user with thousands of rated items must not start last
@@ -1149,10 +1174,12 @@ k_score_f32(const uint32_t* __restrict__ Hf, int32_t I_c, int32_t ld, int32_t ra
     const int32_t n = rowptr[rank + 1] - e0;
 
     if (threadIdx.x < SCOREH_TILE / 32) s_rated[threadIdx.x] = 0u;
-    float b[4], p[4];
+    float b[4];
     int ex[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) { b[q] = (i + q < I_c) ? (float)(c_b[slot0 + i + q] * plane_scale) : 0.0f; p[q] = 1.0f; ex[q] = 0; }
+    for (int q = 0; q < 4; q++) { b[q] = (i + q < I_c) ? (float)(c_b[slot0 + i + q] * plane_scale) : 0.0f; ex[q] = 0; }
+    const f32x2_t b01 = pack_f32x2(b[0], b[1]), b23 = pack_f32x2(b[2], b[3]);
+    f32x2_t p01 = pack_f32x2(1.0f, 1.0f), p23 = p01;
     const uint32_t* __restrict__ Hc = Hf + i;
 
     for (int32_t base = 0; base < n; base += SCORE_CHUNK) {
@@ -1160,8 +1187,7 @@ k_score_f32(const uint32_t* __restrict__ Hf, int32_t I_c, int32_t ld, int32_t ra
         __syncthreads();
         for (int32_t k = threadIdx.x; k < cnt; k += SCORE_THREADS) {
             const int32_t j = csr_loc[e0 + base + k];
-            s_j[k] = j;
-            s_c[k] = (float)csr_c[e0 + base + k];
+            s_jc[k] = make_uint2((uint32_t)j, __float_as_uint((float)csr_c[e0 + base + k]));
             const int32_t d = j - tile0;
             if (d >= 0 && d < SCOREH_TILE) atomicOr(&s_rated[d >> 5], 1u << (d & 31));
         }
@@ -1169,34 +1195,33 @@ k_score_f32(const uint32_t* __restrict__ Hf, int32_t I_c, int32_t ld, int32_t ra
         int32_t k = 0;
         for (; k + 8 <= cnt; k += 8) {
             uint4 h[8];
-#pragma unroll
-            for (int q = 0; q < 8; q++) h[q] = __ldg(reinterpret_cast<const uint4*>(Hc + (size_t)s_j[k + q] * ld));
+            uint32_t cb[8];
 #pragma unroll
             for (int q = 0; q < 8; q++) {
-                const float c = s_c[k + q];
-                p[0] *= fmaf(b[0], c, __uint_as_float(h[q].x));
-                p[1] *= fmaf(b[1], c, __uint_as_float(h[q].y));
-                p[2] *= fmaf(b[2], c, __uint_as_float(h[q].z));
-                p[3] *= fmaf(b[3], c, __uint_as_float(h[q].w));
-                if ((q + 1) % LF == 0) {
+                const uint2 jc = s_jc[k + q];
+                cb[q] = jc.y;
+                h[q] = __ldg(reinterpret_cast<const uint4*>(Hc + (size_t)jc.x * ld));
+            }
 #pragma unroll
-                    for (int z = 0; z < 4; z++) peel_exponent_f(p[z], ex[z]);
-                }
+            for (int q = 0; q < 8; q++) {
+                const f32x2_t c2 = pack_u32x2(cb[q], cb[q]);
+                p01 = fmul2(p01, ffma2(b01, c2, pack_u32x2(h[q].x, h[q].y)));     // p *= fmaf(b, c, h), two candidates per instruction
+                p23 = fmul2(p23, ffma2(b23, c2, pack_u32x2(h[q].z, h[q].w)));
+                if ((q + 1) % LF == 0) { peel_exponent_f2(p01, ex[0], ex[1]); peel_exponent_f2(p23, ex[2], ex[3]); }
             }
         }
         for (; k < cnt; k++) {
-            const uint4 h = __ldg(reinterpret_cast<const uint4*>(Hc + (size_t)s_j[k] * ld));
-            const float c = s_c[k];
-            p[0] *= fmaf(b[0], c, __uint_as_float(h.x));
-            p[1] *= fmaf(b[1], c, __uint_as_float(h.y));
-            p[2] *= fmaf(b[2], c, __uint_as_float(h.z));
-            p[3] *= fmaf(b[3], c, __uint_as_float(h.w));
-            if (((k & 7) + 1) % LF == 0 || k + 1 == cnt) {
-#pragma unroll
-                for (int z = 0; z < 4; z++) peel_exponent_f(p[z], ex[z]);
-            }
+            const uint2 jc = s_jc[k];
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(Hc + (size_t)jc.x * ld));
+            const f32x2_t c2 = pack_u32x2(jc.y, jc.y);
+            p01 = fmul2(p01, ffma2(b01, c2, pack_u32x2(h.x, h.y)));
+            p23 = fmul2(p23, ffma2(b23, c2, pack_u32x2(h.z, h.w)));
+            if (((k & 7) + 1) % LF == 0 || k + 1 == cnt) { peel_exponent_f2(p01, ex[0], ex[1]); peel_exponent_f2(p23, ex[2], ex[3]); }
         }
     }
+    float p[4];
+    p[0] = __uint_as_float((uint32_t)p01); p[1] = __uint_as_float((uint32_t)(p01 >> 32));
+    p[2] = __uint_as_float((uint32_t)p23); p[3] = __uint_as_float((uint32_t)(p23 >> 32));
     __syncthreads();
     const double pvpi = __dsub_rn(__dmul_rn((double)(n - 1), log_items), __dmul_rn((double)n, log_K));
     const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
