@@ -587,20 +587,24 @@ extern "C" int fy_nmf_run(fy_nmf_ctx* ctx) {
         const bool norm_on = ctx->prm.apply_normalization != 0 && ctx->prm.mode == 1 && nf != 0;
         const bool norm_const = !norm_on || nf == 1 || nf == -1;
         const bool use_graph = norm_const && n_iter >= 4;
-        if (use_graph && !ctx->graph[0]) {
-            // the launch-bound inner loop (8-10 small kernels) is captured once per direction of the ping-pong
-            for (int dir = 0; dir < 2; dir++) {
-                cudaGraph_t g = nullptr;
-                const int64_t keep = ctx->launches;
-                NCK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-                try { enqueue_iteration(ctx, dir, dir ^ 1, norm_on ? 1 : 0); }
-                catch (...) { cudaStreamEndCapture(st, &g); if (g) cudaGraphDestroy(g); throw; }
-                NCK(cudaStreamEndCapture(st, &g));
-                ctx->launches = keep;                 // captured, not launched
-                const cudaError_t e = cudaGraphInstantiate(&ctx->graph[dir], g, 0);
-                cudaGraphDestroy(g);
-                NCK(e);
-            }
+        if (use_graph && !(ctx->graph[0] && ctx->graph[1])) {
+            // the launch-bound inner loop (8-10 small kernels) is captured once per direction of the ping-pong; a failure
+            // half way (direction 0 captured, direction 1 not) must not leave a null handle behind for the next run
+            ctx->drop_graphs();
+            try {
+                for (int dir = 0; dir < 2; dir++) {
+                    cudaGraph_t g = nullptr;
+                    const int64_t keep = ctx->launches;
+                    NCK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                    try { enqueue_iteration(ctx, dir, dir ^ 1, norm_on ? 1 : 0); }
+                    catch (...) { cudaStreamEndCapture(st, &g); if (g) cudaGraphDestroy(g); throw; }
+                    NCK(cudaStreamEndCapture(st, &g));
+                    ctx->launches = keep;                 // captured, not launched
+                    const cudaError_t e = cudaGraphInstantiate(&ctx->graph[dir], g, 0);
+                    cudaGraphDestroy(g);
+                    NCK(e);
+                }
+            } catch (...) { ctx->drop_graphs(); throw; }
         }
         int64_t graph_kernels = 0;
         for (int it = 1; it <= n_iter; it++) {

@@ -1213,6 +1213,12 @@ extern "C" int fy_rm2_run(fy_rm2_ctx* ctx) {
 
 extern "C" int32_t fy_rm2_max_item(const fy_rm2_ctx* ctx) { return !ctx ? -1 : (ctx->kids.empty() ? ctx->max_item : ctx->kids[0]->max_item); }
 
+extern "C" int64_t fy_rm2_user_count(const fy_rm2_ctx* ctx) {
+    if (!ctx) return -1;
+    if (!ctx->kids.empty()) return ctx->kids[0]->have_clustering ? ctx->kids[0]->n_users : -1;
+    return ctx->have_clustering || ctx->have_results ? ctx->n_users : -1;
+}
+
 extern "C" int fy_rm2_stats(fy_rm2_ctx* ctx, double* user_sum, double* item_prob, double* total) {
     if (!ctx) return FY_E_ARG;
     if (!ctx->have_results) return ctx->fail(FY_E_STATE, "fy_rm2_stats needs a successful fy_rm2_run");

@@ -12,7 +12,26 @@
 // IntPairWritable (two big-endian ints); neither library is vendored under /root/reference and the
 // reference holds no serialized fixture (its tests write them at run time), so the layout below is a
 // restatement of the published formats -- PARITY UNPINNED at the byte level; tests check round trips
-// and an independently assembled byte image.
+// and an independently assembled byte image.  What each piece restates (Apache sources, from memory of the
+// published code; line numbers are those of the tagged releases and may be off by a few lines):
+//   header + records : hadoop-1.2.1 src/core/org/apache/hadoop/io/SequenceFile.java -- VERSION = {'S','E','Q',6} (:~190),
+//                      Writer.writeFileHeader (:~980: version, Text key class, Text value class, compression flags,
+//                      Metadata, sync), Writer.append(Object, Object) (:~1010: checkAndWriteSync, int recordLength,
+//                      int keyLength, key, value), SYNC_ESCAPE = -1, SYNC_HASH_SIZE = 16, SYNC_SIZE = 20,
+//                      SYNC_INTERVAL = 100 * SYNC_SIZE (:~200), checkAndWriteSync (:~990: a marker once
+//                      out.getPos() >= lastSyncPos + SYNC_INTERVAL)
+//   Text / VInt      : hadoop-1.2.1 .../io/Text.java writeString / write (:~280: VInt length + UTF-8),
+//                      .../io/WritableUtils.java writeVLong / readVLong / decodeVIntSize (:~260-330)
+//   IntPairWritable  : mahout-core-0.8 org/apache/mahout/common/IntPairWritable.java -- a 2 * 4 byte array b[]; set() -> putInt
+//                      stores each int most significant byte first (b[i] = (byte) (value >> j), j = 24, 16, 8, 0); the sign is
+//                      handled by the raw comparator (compareInts), not by the stored bytes; write(DataOutput) = out.write(b)
+//   VectorWritable   : mahout-core-0.8 org/apache/mahout/math/VectorWritable.java writeVector (:~100: flag byte
+//                      FLAG_DENSE 0x01 | FLAG_SEQUENTIAL 0x02 | FLAG_NAMED 0x04 | FLAG_LAX_PRECISION 0x08, VInt size,
+//                      dense: doubles; sparse: VInt nondefault count, then (VInt index [delta-coded if sequential], value))
+//   MapFile          : hadoop-1.2.1 .../io/MapFile.java -- directory with DATA_FILE_NAME "data" + INDEX_FILE_NAME "index"
+//                      (:~50), Writer.append (:~190: every indexInterval = 128-th key goes to the index with the data
+//                      file position as a LongWritable)
+// If a byte differs from what a real Hadoop writer emits, these are the places to compare.
 //
 //   header : 'S' 'E' 'Q' 6 | Text keyClass | Text valueClass | bool compressed | bool blockCompressed |
 //            int32 metadataCount (+ Text pairs) | 16-byte sync marker
@@ -71,7 +90,7 @@ bool get_vint(const uint8_t*& p, const uint8_t* end, int64_t& out) {
     if (first >= -112) { out = first; return true; }
     const bool neg = first < -120;
     const int len = neg ? -(first + 120) : -(first + 112);
-    if (p + len > end) return false;
+    if ((size_t)len > (size_t)(end - p)) return false;
     int64_t v = 0;
     for (int k = 0; k < len; k++) v = (v << 8) | *p++;
     out = neg ? (v ^ -1LL) : v;
@@ -84,7 +103,7 @@ void put_text(std::vector<uint8_t>& o, const char* s) {
 }
 bool get_text(const uint8_t*& p, const uint8_t* end, std::string& out) {
     int64_t n;
-    if (!get_vint(p, end, n) || n < 0 || p + n > end) return false;
+    if (!get_vint(p, end, n) || n < 0 || (uint64_t)n > (uint64_t)(end - p)) return false;
     out.assign((const char*)p, (size_t)n);
     p += n;
     return true;
@@ -183,26 +202,26 @@ int scan_file(const std::string& path, const char* key_class, const char* val_cl
     std::string kc, vc;
     if (!get_text(p, end, kc) || !get_text(p, end, vc)) return fail(FY_E_ARG, "%s: truncated header", path.c_str());
     if (kc != key_class || vc != val_class) return fail(FY_E_ARG, "%s: unexpected key/value classes (%s)", path.c_str(), (kc + ", " + vc).c_str());
-    if (p + 2 > end) return fail(FY_E_ARG, "%s: truncated header", path.c_str());
+    if ((size_t)(end - p) < 2) return fail(FY_E_ARG, "%s: truncated header", path.c_str());
     if (p[0] != 0 || p[1] != 0) return fail(FY_E_UNSUPPORTED, "%s: compressed SequenceFiles are not supported", path.c_str());
     p += 2;
-    if (p + 4 > end) return fail(FY_E_ARG, "%s: truncated header", path.c_str());
+    if ((size_t)(end - p) < 4) return fail(FY_E_ARG, "%s: truncated header", path.c_str());
     const uint32_t meta = get_be32(p); p += 4;
     for (uint32_t k = 0; k < meta; k++) { std::string a, b; if (!get_text(p, end, a) || !get_text(p, end, b)) return fail(FY_E_ARG, "%s: bad metadata", path.c_str()); }
-    if (p + 16 > end) return fail(FY_E_ARG, "%s: truncated header", path.c_str());
+    if ((size_t)(end - p) < 16) return fail(FY_E_ARG, "%s: truncated header", path.c_str());
     uint8_t sync[16];
     memcpy(sync, p, 16); p += 16;
     while (p < end) {
-        if (p + 4 > end) return fail(FY_E_ARG, "%s: truncated record", path.c_str());
+        if ((size_t)(end - p) < 4) return fail(FY_E_ARG, "%s: truncated record", path.c_str());
         const uint32_t len = get_be32(p); p += 4;
         if (len == 0xffffffffu) {                                 // sync escape
-            if (p + 16 > end || memcmp(p, sync, 16) != 0) return fail(FY_E_ARG, "%s: corrupt sync marker", path.c_str());
+            if ((size_t)(end - p) < 16 || memcmp(p, sync, 16) != 0) return fail(FY_E_ARG, "%s: corrupt sync marker", path.c_str());
             p += 16;
             continue;
         }
-        if (p + 4 > end) return fail(FY_E_ARG, "%s: truncated record", path.c_str());
+        if ((size_t)(end - p) < 4) return fail(FY_E_ARG, "%s: truncated record", path.c_str());
         const uint32_t klen = get_be32(p); p += 4;
-        if (klen > len || p + len > end) return fail(FY_E_ARG, "%s: corrupt record length", path.c_str());
+        if (klen > len || (uint64_t)len > (uint64_t)(end - p)) return fail(FY_E_ARG, "%s: corrupt record length", path.c_str());
         rc = rec(p, (int)klen, p + klen, (int)(len - klen));
         if (rc != FY_OK) return rc;
         p += len;
@@ -493,8 +512,8 @@ extern "C" int fy_seq_read_int_vector(const char* path, int32_t** key, double** 
             const size_t base = vs.size();
             vs.resize(base + size, 0.0);
             auto element = [&](double& out) -> bool {
-                if (lax) { if (p + 4 > end) return false; const uint32_t b = get_be32(p); p += 4; float x; memcpy(&x, &b, 4); out = x; }
-                else { if (p + 8 > end) return false; const uint64_t b = get_be64(p); p += 8; memcpy(&out, &b, 8); }
+                if (lax) { if ((size_t)(end - p) < 4) return false; const uint32_t b = get_be32(p); p += 4; float x; memcpy(&x, &b, 4); out = x; }
+                else { if ((size_t)(end - p) < 8) return false; const uint64_t b = get_be64(p); p += 8; memcpy(&out, &b, 8); }
                 return true;
             };
             if (dense) {

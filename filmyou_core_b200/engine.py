@@ -28,7 +28,7 @@ EXPORTS = [
     "fy_rm2_stats", "fy_rm2_result_count", "fy_rm2_users_scored", "fy_rm2_results", "fy_rm2_results_device", "fy_rm2_score_group",
     "fy_rm2_get_profile", "fy_cooc_counts", "fy_cooc_topk", "fy_knn_neighbours",
     "fy_rm2_result_row_count", "fy_rm2_result_rows", "fy_rm2_nccl_unique_id", "fy_rm2_comm_init", "fy_rm2_comm_destroy",
-    "fy_rm2_shard_bounds", "fy_rm2_probe_plane_read",
+    "fy_rm2_shard_bounds", "fy_rm2_probe_plane_read", "fy_rm2_user_count",
 ]
 # include/filmyou_seqfile.h
 SEQ_EXPORTS = [
@@ -79,17 +79,39 @@ def sources():
     return sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cpp")))
 
 
-def build_library(force=False, verbose=False):
-    """nvcc cross-compiles for sm_100a without a GPU (seconds)."""
-    deps = sources() + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh")]
+def source_hash():
+    """sha256 over every source and header the library is built from (file names + contents)."""
+    import hashlib
+    deps = sources() + sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh"))
     deps += [os.path.join(_HERE, "..", "include", h) for h in ("filmyou_rm2.h", "filmyou_seqfile.h", "filmyou_nmf.h")]
-    if not force and os.path.exists(_SO) and all(os.path.getmtime(d) <= os.path.getmtime(_SO) for d in deps):
+    h = hashlib.sha256()
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def build_library(force=False, verbose=False):
+    """nvcc cross-compiles for sm_100a without a GPU (about a minute).  The library is rebuilt unless a stamp file next
+    to it records the hash of exactly these sources (mtimes do not survive a copy to the GPU box and prove nothing);
+    says which of the two happened."""
+    want = source_hash()
+    stamp = _SO + ".srchash"
+    have = open(stamp).read().strip() if os.path.exists(stamp) else ""
+    if not force and os.path.exists(_SO) and have == want:
+        if verbose:
+            print("libfilmyou_rm2.so: reused (source hash %s matches the stamp)" % want[:16])
         return _SO
     cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC", "-shared", "-o", _SO] + sources()
+           "-Xcompiler", "-fPIC", "-shared", "-o", _SO] + sources() + ["-ldl"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    with open(stamp, "w") as f:
+        f.write(want + "\n")
+    if verbose:
+        print("libfilmyou_rm2.so: compiled from source (source hash %s)" % want[:16])
     return _SO
 
 
@@ -134,6 +156,8 @@ def load_library():
     L.fy_rm2_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
     L.fy_rm2_comm_destroy.argtypes = [vp]
     L.fy_rm2_shard_bounds.argtypes = [vp, i32p]
+    L.fy_rm2_user_count.argtypes = [vp]
+    L.fy_rm2_user_count.restype = C.c_int64
     L.fy_rm2_probe_plane_read.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, f64p, f64p]
     L.fy_cooc_counts.argtypes = [vp, C.c_int32, C.c_int32, i32p, f64p]
     L.fy_cooc_topk.argtypes = [vp, C.c_int32, i32p, i32p, i32p]

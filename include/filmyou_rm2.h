@@ -119,6 +119,7 @@ int fy_rm2_run(fy_rm2_ctx* ctx);
 /* rm2/userSum (in the order users were given to fy_rm2_set_clustering), rm2/itemColl
  * (indexed by item id, 0..max_item) and the truncated global total (M/rm/RM2Job.java:95). */
 int32_t fy_rm2_max_item(const fy_rm2_ctx* ctx);
+int64_t fy_rm2_user_count(const fy_rm2_ctx* ctx);      /* users given to fy_rm2_set_clustering (-1 before) */
 int fy_rm2_stats(fy_rm2_ctx* ctx, double* user_sum, double* item_prob, double* total);
 
 /* Results of the last run: packed triples grouped by (cluster, user id), descending score inside a

@@ -19,8 +19,13 @@ public final class RM2Native {
     private RM2Native() {
     }
 
+    /**
+     * @param nGpus 0/1: this context drives <code>device</code>; n &gt; 1: ONE context drives devices device..device+n-1
+     *              (users sharded over them, results concatenated) -- shardRank/shardCount must then be 0/1.
+     * @throws RuntimeException when no usable B200 exists or a parameter is invalid (also returns 0)
+     */
     public static native long create(double lambda, int numberOfItems, int numberOfRecommendations,
-            int filterUsers, int device, int shardRank, int shardCount);
+            int filterUsers, int device, int shardRank, int shardCount, int nGpus);
 
     public static native int setRatings(long ctx, IntBuffer user, IntBuffer item, FloatBuffer score, long nnz);
 
@@ -38,6 +43,11 @@ public final class RM2Native {
 
     public static native int results(long ctx, IntBuffer user, IntBuffer item, DoubleBuffer score64,
             FloatBuffer score32, IntBuffer cluster);
+
+    /** One (user, cluster, count) record per scored user, in the order of the triples of {@link #results}. */
+    public static native long resultRowCount(long ctx);
+
+    public static native int resultRows(long ctx, IntBuffer user, IntBuffer cluster, IntBuffer count);
 
     public static native int stats(long ctx, DoubleBuffer userSum, DoubleBuffer itemProb, DoubleBuffer total);
 

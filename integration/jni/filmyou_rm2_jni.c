@@ -16,26 +16,44 @@
 #include "filmyou_nmf.h"
 #include "filmyou_rm2.h"
 
+#include <stdio.h>
+
 #define BUF(b) ((b) ? (*env)->GetDirectBufferAddress(env, (b)) : NULL)
+/* A sizing mistake on the Java side must not become an out-of-bounds access inside the JVM: every buffer's capacity
+ * (in elements of its own type, as GetDirectBufferCapacity reports it for a view buffer) is checked against the count
+ * the call will touch; a non-direct buffer (address NULL, capacity -1) fails the same way. */
+#define NEED(b, n) do { if ((b) && ((*env)->GetDirectBufferAddress(env, (b)) == NULL || (*env)->GetDirectBufferCapacity(env, (b)) < (jlong)(n))) return FY_E_ARG; } while (0)
+#define NEED_NN(b, n) do { if (!(b)) return FY_E_ARG; NEED(b, n); } while (0)
+
+static void throw_runtime(JNIEnv* env, const char* what, int code) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "%s failed: fy_status %d (no usable B200, or bad parameters)", what, code);
+    jclass ex = (*env)->FindClass(env, "java/lang/RuntimeException");       /* RM2Job.java:265-268: a failed job throws */
+    if (ex) (*env)->ThrowNew(env, ex, msg);
+}
 #define RM2(h) ((fy_rm2_ctx*)(intptr_t)(h))
 #define NMF(h) ((fy_nmf_ctx*)(intptr_t)(h))
 
 /* ---- es.udc.fi.dc.irlab.rm.RM2Native ---- */
 JNIEXPORT jlong JNICALL Java_es_udc_fi_dc_irlab_rm_RM2Native_create(JNIEnv* env, jclass cls, jdouble lambda, jint numberOfItems,
                                                                     jint numberOfRecommendations, jint filterUsers, jint device,
-                                                                    jint shardRank, jint shardCount) {
-    (void)env; (void)cls;
+                                                                    jint shardRank, jint shardCount, jint nGpus) {
+    (void)cls;
     fy_rm2_params p;
     fy_rm2_default_params(&p);
     p.lambda = lambda; p.number_of_items = numberOfItems; p.top_n = numberOfRecommendations; p.filter_users = filterUsers;
-    p.device = device; p.shard_rank = shardRank; p.shard_count = shardCount;
+    p.device = device; p.shard_rank = shardRank; p.shard_count = shardCount; p.n_gpus = nGpus;
     fy_rm2_ctx* ctx = NULL;
-    return fy_rm2_create(&ctx, &p) == FY_OK ? (jlong)(intptr_t)ctx : 0;
+    const int rc = fy_rm2_create(&ctx, &p);
+    if (rc != FY_OK) { throw_runtime(env, "fy_rm2_create", rc); return 0; }
+    return (jlong)(intptr_t)ctx;
 }
 
 JNIEXPORT jint JNICALL Java_es_udc_fi_dc_irlab_rm_RM2Native_setRatings(JNIEnv* env, jclass cls, jlong h, jobject user, jobject item,
                                                                        jobject score, jlong nnz) {
     (void)cls;
+    if (nnz < 0) return FY_E_ARG;
+    NEED_NN(user, nnz); NEED_NN(item, nnz); NEED_NN(score, nnz);
     return fy_rm2_set_ratings(RM2(h), (const int32_t*)BUF(user), (const int32_t*)BUF(item), (const float*)BUF(score), nnz);
 }
 
@@ -43,6 +61,8 @@ JNIEXPORT jint JNICALL Java_es_udc_fi_dc_irlab_rm_RM2Native_setClustering(JNIEnv
                                                                           jobject cluster, jlong nUsers, jobject clusterSize,
                                                                           jint nClusters) {
     (void)cls;
+    if (nUsers < 0 || nClusters < 0) return FY_E_ARG;
+    NEED_NN(user, nUsers); NEED_NN(cluster, nUsers); NEED_NN(clusterSize, nClusters);
     return fy_rm2_set_clustering(RM2(h), (const int32_t*)BUF(user), (const int32_t*)BUF(cluster), nUsers,
                                  (const int32_t*)BUF(clusterSize), nClusters);
 }
@@ -57,6 +77,9 @@ JNIEXPORT jint JNICALL Java_es_udc_fi_dc_irlab_rm_RM2Native_scoreGroup(JNIEnv* e
                                                                        jint nGroupUsers, jobject rUser, jobject rItem, jobject rScore,
                                                                        jlong nnz, jobject itemProb, jint maxItem) {
     (void)cls;
+    if (nGroupUsers < 0 || nnz < 0 || maxItem < 0) return FY_E_ARG;
+    NEED_NN(groupUser, nGroupUsers); NEED_NN(groupUserSum, nGroupUsers);
+    NEED_NN(rUser, nnz); NEED_NN(rItem, nnz); NEED_NN(rScore, nnz); NEED_NN(itemProb, (jlong)maxItem + 1);
     return fy_rm2_score_group(RM2(h), cluster, split, nSplits, (const int32_t*)BUF(groupUser), (const double*)BUF(groupUserSum),
                               nGroupUsers, (const int32_t*)BUF(rUser), (const int32_t*)BUF(rItem), (const float*)BUF(rScore), nnz,
                               (const double*)BUF(itemProb), maxItem);
@@ -70,6 +93,9 @@ JNIEXPORT jlong JNICALL Java_es_udc_fi_dc_irlab_rm_RM2Native_resultCount(JNIEnv*
 JNIEXPORT jint JNICALL Java_es_udc_fi_dc_irlab_rm_RM2Native_results(JNIEnv* env, jclass cls, jlong h, jobject user, jobject item,
                                                                     jobject score64, jobject score32, jobject cluster) {
     (void)cls;
+    const jlong n = fy_rm2_result_count(RM2(h));
+    if (n < 0) return FY_E_STATE;
+    NEED(user, n); NEED(item, n); NEED(score64, n); NEED(score32, n); NEED(cluster, n);
     return fy_rm2_results(RM2(h), (int32_t*)BUF(user), (int32_t*)BUF(item), (double*)BUF(score64), (float*)BUF(score32),
                           (int32_t*)BUF(cluster));
 }
@@ -77,7 +103,24 @@ JNIEXPORT jint JNICALL Java_es_udc_fi_dc_irlab_rm_RM2Native_results(JNIEnv* env,
 JNIEXPORT jint JNICALL Java_es_udc_fi_dc_irlab_rm_RM2Native_stats(JNIEnv* env, jclass cls, jlong h, jobject userSum, jobject itemProb,
                                                                   jobject total) {
     (void)cls;
+    const jlong nu = fy_rm2_user_count(RM2(h));
+    if (nu < 0) return FY_E_STATE;
+    NEED(userSum, nu); NEED(itemProb, (jlong)fy_rm2_max_item(RM2(h)) + 1); NEED(total, 1);
     return fy_rm2_stats(RM2(h), (double*)BUF(userSum), (double*)BUF(itemProb), (double*)BUF(total));
+}
+
+JNIEXPORT jlong JNICALL Java_es_udc_fi_dc_irlab_rm_RM2Native_resultRowCount(JNIEnv* env, jclass cls, jlong h) {
+    (void)env; (void)cls;
+    return fy_rm2_result_row_count(RM2(h));
+}
+
+JNIEXPORT jint JNICALL Java_es_udc_fi_dc_irlab_rm_RM2Native_resultRows(JNIEnv* env, jclass cls, jlong h, jobject user, jobject cluster,
+                                                                       jobject count) {
+    (void)cls;
+    const jlong n = fy_rm2_result_row_count(RM2(h));
+    if (n < 0) return FY_E_STATE;
+    NEED(user, n); NEED(cluster, n); NEED(count, n);
+    return fy_rm2_result_rows(RM2(h), (int32_t*)BUF(user), (int32_t*)BUF(cluster), (int32_t*)BUF(count));
 }
 
 JNIEXPORT jint JNICALL Java_es_udc_fi_dc_irlab_rm_RM2Native_maxItem(JNIEnv* env, jclass cls, jlong h) {
@@ -100,19 +143,23 @@ JNIEXPORT jlong JNICALL Java_es_udc_fi_dc_irlab_nmf_ppc_NmfNative_create(JNIEnv*
                                                                          jint numberOfItems, jint numberOfClusters,
                                                                          jint numberOfIterations, jint normalizationFrequency,
                                                                          jint idBase, jint device) {
-    (void)env; (void)cls;
+    (void)cls;
     fy_nmf_params p;
     fy_nmf_default_params(&p);
     p.mode = mode; p.number_of_users = numberOfUsers; p.number_of_items = numberOfItems; p.number_of_clusters = numberOfClusters;
     p.number_of_iterations = numberOfIterations; p.normalization_frequency = normalizationFrequency; p.id_base = idBase;
     p.device = device;
     fy_nmf_ctx* ctx = NULL;
-    return fy_nmf_create(&ctx, &p) == FY_OK ? (jlong)(intptr_t)ctx : 0;
+    const int rc = fy_nmf_create(&ctx, &p);
+    if (rc != FY_OK) { throw_runtime(env, "fy_nmf_create", rc); return 0; }
+    return (jlong)(intptr_t)ctx;
 }
 
 JNIEXPORT jint JNICALL Java_es_udc_fi_dc_irlab_nmf_ppc_NmfNative_setRatings(JNIEnv* env, jclass cls, jlong h, jobject user, jobject item,
                                                                             jobject score, jlong nnz) {
     (void)cls;
+    if (nnz < 0) return FY_E_ARG;
+    NEED_NN(user, nnz); NEED_NN(item, nnz); NEED_NN(score, nnz);
     return fy_nmf_set_ratings(NMF(h), (const int32_t*)BUF(user), (const int32_t*)BUF(item), (const float*)BUF(score), nnz);
 }
 

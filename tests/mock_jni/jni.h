@@ -24,5 +24,7 @@ struct JNINativeInterface_ {
     void* (*GetDirectBufferAddress)(JNIEnv* env, jobject buf);
     jlong (*GetDirectBufferCapacity)(JNIEnv* env, jobject buf);
     jstring (*NewStringUTF)(JNIEnv* env, const char* utf);
+    jclass (*FindClass)(JNIEnv* env, const char* name);
+    jint (*ThrowNew)(JNIEnv* env, jclass cls, const char* message);
 };
 #endif

@@ -58,6 +58,7 @@ def test_stub_through_a_fake_jnienv_matches_the_oracles(tmp_path, golden, golden
     lines += ["%d %d %r" % (u, i, float(s)) for u, i, s in zip(r.user, r.item, r.score)]
     lines += ["%d %d" % (u, c) for u, c in zip(r.cl_user, r.cl_cluster)]
     lines += ["%d" % c for c in r.cluster_size]
+    lines.append("%d %d" % (golden["clusterSplit"], golden["splitSize"]))
     p = json.load(open(os.path.join(ROOT, "tests", "golden", "ppc_test_data.json")))
     pu, pi, ps = norc.coo_from_dense(p["A"])
     lines.append("%d %d %d %d %d" % (p["numberOfUsers"], p["numberOfItems"], p["numberOfClusters"], 10, len(pu)))
@@ -75,7 +76,25 @@ def test_stub_through_a_fake_jnienv_matches_the_oracles(tmp_path, golden, golden
     assert np.max(np.abs(got[:, 2] - want["score64"]) / np.abs(want["score64"])) < 1e-9
     assert rows[1 + n].startswith("state -8 ")                       # FY_E_STATE and its message cross the stub
     assert "fy_rm2_run needs" in rows[1 + n]
-    k0 = 2 + n
+    assert rows[2 + n] == "capacity -1"                              # an undersized direct buffer is refused (FY_E_ARG)
+    assert rows[3 + n].startswith("create 0 java/lang/RuntimeException: fy_rm2_create failed")
+    # fine seam through the stub: every "c-split-nSplits" group of TestHDFSRM2's configuration (clusterSplit=5, splitSize=3),
+    # bit for bit the coarse seam's triples, each user in the split its id selects (AbstractRM2Reducer.java:203-205)
+    assert rows[4 + n] == "fine"
+    k1 = 5 + n
+    fine = []
+    while not rows[k1].startswith("fine-end"):
+        fine.append([float(x) for x in rows[k1].split()]); k1 += 1
+    fine = np.array(fine)
+    assert int(rows[k1].split()[1]) == len(fine) == n
+    coarse = {(int(a), int(b)): (c, int(d)) for a, b, c, d in got}
+    sizes = dict(zip(range(len(r.cluster_size)), r.cluster_size.tolist()))
+    for uu, ii, sc, cl_, sp in fine:
+        assert coarse[(int(uu), int(ii))] == (sc, int(cl_))
+        K = sizes[int(cl_)]
+        n_splits = -(-K // golden["splitSize"]) if K >= golden["clusterSplit"] else 1
+        assert int(uu) % n_splits == int(sp)
+    k0 = k1 + 1
     assert rows[k0] == "ppc 30 10"
     H = np.array([float(x) for x in rows[k0 + 1:k0 + 1 + 300]]).reshape(30, 10)
     cl = np.array([int(x) for x in rows[k0 + 301:k0 + 331]])
