@@ -132,6 +132,9 @@ struct fy_rm2_ctx {
     DBuf<int32_t> row_user, row_cluster;
     void* nccl_comm = nullptr;                      // ncclComm_t, attached by fy_rm2_comm_init
     std::vector<fy_rm2_ctx*> kids;                  // n_gpus > 1: one child context per device
+    std::vector<int32_t> owner_rank;                // neighbour-list mode (child context): the one scored rank of each virtual cluster
+    fy_rm2_ctx* nbr_child = nullptr;                // lazily created by fy_rm2_run_neighbours
+    fy_rm2_ctx* view = nullptr;                     // results of the last call live in this (neighbour-list) child context
     std::vector<int64_t> kid_off;
     DBuf<int32_t> p_user, p_item, p_cluster;
     DBuf<double> p_s64;
@@ -268,6 +271,7 @@ extern "C" void fy_rm2_destroy(fy_rm2_ctx* ctx) {
     if (!ctx) return;
     for (fy_rm2_ctx* k : ctx->kids) fy_rm2_destroy(k);
     ctx->kids.clear();
+    if (ctx->nbr_child) { fy_rm2_destroy(ctx->nbr_child); ctx->nbr_child = nullptr; }
     fy_rm2_comm_destroy(ctx);
     cudaSetDevice(ctx->prm.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -337,6 +341,7 @@ extern "C" int fy_rm2_set_ratings(fy_rm2_ctx* ctx, const int32_t* user, const in
         ctx->have_results = false;
         return fan_out(ctx, [&](fy_rm2_ctx* k, size_t) { return fy_rm2_set_ratings(k, user, item, score, nnz); });
     }
+    ctx->view = nullptr;
     return guarded(ctx, [&]() { ctx->use_ext = false; return upload_ratings(ctx, user, item, score, nnz); });
 }
 
@@ -968,7 +973,9 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
         int n_touched = 0, n_batches = 0;
         for (int32_t c = 0; c < KC; c++) {
             const int32_t cs = ctx->h_cstart[c], ce = ctx->h_cstart[c + 1];
-            const int32_t r0 = std::max(cs, ub), r1 = std::min(ce, ue), I_c = ctx->h_icount[c];
+            int32_t r0 = std::max(cs, ub), r1 = std::min(ce, ue);
+            const int32_t I_c = ctx->h_icount[c];
+            if (!ctx->owner_rank.empty()) { r0 = std::max(r0, ctx->owner_rank[c]); r1 = std::min(r1, ctx->owner_rank[c] + 1); }
             if (r1 <= r0 || I_c <= 0) continue;
             int32_t ld, slice_w, chunk_w, nchunk, n_bound;
             h_geometry(I_c, ld, slice_w, chunk_w, nchunk, n_bound);
@@ -995,7 +1002,9 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     bool h_used[2] = {false, false}, s_used[2] = {false, false};
     for (int32_t c = 0; c < KC; c++) {
         const int32_t cs = ctx->h_cstart[c], ce = ctx->h_cstart[c + 1];
-        const int32_t r0 = std::max(cs, ub), r1 = std::min(ce, ue);
+        int32_t r0 = std::max(cs, ub), r1 = std::min(ce, ue);
+        // neighbour-list mode: the cluster is {u} + N(u) and only its owner u is scored (fy_rm2_run_neighbours)
+        if (!ctx->owner_rank.empty()) { r0 = std::max(r0, ctx->owner_rank[c]); r1 = std::min(r1, ctx->owner_rank[c] + 1); }
         if (r1 <= r0) continue;
         const int32_t K_c = ce - cs, I_c = ctx->h_icount[c], slot0 = ctx->h_item_off[c];
         if (I_c <= 0) continue;
@@ -1180,6 +1189,7 @@ static int run_pipeline(fy_rm2_ctx* ctx) {
 
 extern "C" int fy_rm2_run(fy_rm2_ctx* ctx) {
     if (!ctx) return FY_E_ARG;
+    ctx->view = nullptr;
     if (!ctx->kids.empty()) {
         ctx->have_results = false;
         const int rc = fan_out(ctx, [&](fy_rm2_ctx* k, size_t) { return fy_rm2_run(k); });
@@ -1243,11 +1253,12 @@ extern "C" int fy_rm2_stats(fy_rm2_ctx* ctx, double* user_sum, double* item_prob
     });
 }
 
-extern "C" int64_t fy_rm2_result_count(const fy_rm2_ctx* ctx) { return (ctx && ctx->have_results) ? ctx->n_results : -1; }
-extern "C" int64_t fy_rm2_users_scored(const fy_rm2_ctx* ctx) { return (ctx && ctx->have_results) ? ctx->users_scored : -1; }
+extern "C" int64_t fy_rm2_result_count(const fy_rm2_ctx* ctx) { if (ctx && ctx->view) ctx = ctx->view; return (ctx && ctx->have_results) ? ctx->n_results : -1; }
+extern "C" int64_t fy_rm2_users_scored(const fy_rm2_ctx* ctx) { if (ctx && ctx->view) ctx = ctx->view; return (ctx && ctx->have_results) ? ctx->users_scored : -1; }
 
 extern "C" int fy_rm2_results(fy_rm2_ctx* ctx, int32_t* user, int32_t* item, double* score64, float* score32, int32_t* cluster) {
     if (!ctx) return FY_E_ARG;
+    if (ctx->view) { const int rc = fy_rm2_results(ctx->view, user, item, score64, score32, cluster); return rc == FY_OK ? rc : ctx->fail(rc, "%s", ctx->view->err); }
     if (!ctx->have_results) return ctx->fail(FY_E_STATE, "fy_rm2_results needs a successful fy_rm2_run");
     if (!ctx->kids.empty())              // every device copies its slice straight into the caller's buffers, in parallel
         return fan_out(ctx, [&](fy_rm2_ctx* k, size_t i) {
@@ -1284,10 +1295,11 @@ extern "C" int fy_rm2_results_device(fy_rm2_ctx* ctx, const int32_t** user, cons
     return FY_OK;
 }
 
-extern "C" int64_t fy_rm2_result_row_count(const fy_rm2_ctx* ctx) { return (ctx && ctx->have_results) ? ctx->n_result_rows : -1; }
+extern "C" int64_t fy_rm2_result_row_count(const fy_rm2_ctx* ctx) { if (ctx && ctx->view) ctx = ctx->view; return (ctx && ctx->have_results) ? ctx->n_result_rows : -1; }
 
 extern "C" int fy_rm2_result_rows(fy_rm2_ctx* ctx, int32_t* user, int32_t* cluster, int32_t* count) {
     if (!ctx) return FY_E_ARG;
+    if (ctx->view) { const int rc = fy_rm2_result_rows(ctx->view, user, cluster, count); return rc == FY_OK ? rc : ctx->fail(rc, "%s", ctx->view->err); }
     if (!ctx->have_results) return ctx->fail(FY_E_STATE, "fy_rm2_result_rows needs a successful fy_rm2_run");
     if (!ctx->kids.empty()) {
         std::vector<int64_t> ro(ctx->kids.size() + 1, 0);
@@ -1342,8 +1354,140 @@ extern "C" int fy_rm2_probe_plane_read(fy_rm2_ctx* ctx, int32_t n_rows, int32_t 
 
 extern "C" int fy_rm2_get_profile(const fy_rm2_ctx* ctx, fy_rm2_profile* out) {
     if (!ctx || !out) return FY_E_ARG;
+    if (ctx->view) ctx = ctx->view;
     *out = ctx->prof;
     return FY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// f3 / north_star part 1: scoring over EXPLICIT neighbour lists.  buildRecommendations takes `int[] neighbours`
+// (M/rm/AbstractRM2Reducer.java:321-323,342-346); the reference only ever passes "the cluster minus u" (:215-216).
+// Here user u with list N(u) is scored exactly as the reducer would score it in a group made of u and N(u):
+//   K = |N(u)| + 1 (:143,:329), items = everything u or a neighbour rated (:164-174), sum over v in N(u) (:342-346),
+//   p(i|C) and the user sums are the GLOBAL statistics of the rating matrix (jobs RM2-1/2).
+// Implementation: the host expands every listed user into such a group (its members' ratings under fresh virtual user
+// ids, members in ascending real id so that the summation order is the reducer's canonical one), a child context runs
+// the ordinary per-cluster pipeline on the groups with the global statistics passed in (the fine seam's mechanism) and
+// scores only each group's owner; ids are mapped back.  No reference counterpart exists beyond the signature:
+// checked against the neighbour mode of the CPU restatement (tests/), which reproduces the 507 goldens when N(u) = cluster(u) \ {u}.
+// ---------------------------------------------------------------------------------------------
+extern "C" int fy_rm2_run_neighbours(fy_rm2_ctx* ctx, const int32_t* user, const int32_t* neighbour, int32_t k, int64_t n_listed) {
+    if (!ctx) return FY_E_ARG;
+    if (!user || !neighbour || k <= 0 || n_listed <= 0) return ctx->fail(FY_E_ARG, "fy_rm2_run_neighbours: bad argument");
+    if (!ctx->kids.empty() || ctx->prm.shard_count > 1) return ctx->fail(FY_E_UNSUPPORTED, "fy_rm2_run_neighbours on a sharded / n_gpus > 1 context");
+    if (!ctx->have_ratings) return ctx->fail(FY_E_STATE, "fy_rm2_run_neighbours needs fy_rm2_set_ratings first");
+    ctx->view = nullptr;
+    return guarded(ctx, [&]() {
+        CK(cudaSetDevice(ctx->prm.device));
+        const int64_t nnz = ctx->nnz;
+        // ---- the ratings back on the host, positive ones only, by (user id, item id) ----
+        std::vector<int32_t> hu((size_t)nnz), hi((size_t)nnz);
+        std::vector<float> hs((size_t)nnz);
+        CK(cudaMemcpyAsync(hu.data(), ctx->in_user.p, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(hi.data(), ctx->in_item.p, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(hs.data(), ctx->in_score.p, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::vector<int64_t> ord;
+        ord.reserve((size_t)nnz);
+        for (int64_t e = 0; e < nnz; e++) if (hs[e] > 0.0f) ord.push_back(e);            // ScoreByClusterHDFSMapper.java:39-40
+        std::sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) { return hu[a] != hu[b] ? hu[a] < hu[b] : hi[a] < hi[b]; });
+        for (size_t x = 1; x < ord.size(); x++)
+            if (hu[ord[x]] == hu[ord[x - 1]] && hi[ord[x]] == hi[ord[x - 1]]) return ctx->fail(FY_E_DUPLICATE_RATING, "the same (user,item) pair is rated twice");
+        // per user: [begin, end) in ord, and the user sum (ascending item order, DoubleSumReducer.java:31-42)
+        std::vector<int32_t> uid;
+        std::vector<int64_t> ubeg;
+        std::vector<double> usum;
+        const int32_t TI = ctx->max_item + 1;
+        std::vector<double> isum((size_t)TI, 0.0), iprob((size_t)TI, 0.0);
+        long long counter = 0;
+        for (size_t x = 0; x < ord.size();) {
+            size_t y = x;
+            double s = 0.0;
+            while (y < ord.size() && hu[ord[y]] == hu[ord[x]]) { s += (double)hs[ord[y]]; isum[hi[ord[y]]] += (double)hs[ord[y]]; y++; }
+            uid.push_back(hu[ord[x]]); ubeg.push_back((int64_t)x); usum.push_back(s);
+            counter += (long long)s * 100;                                                  // DoubleSumAndCountReducer.java:41
+            x = y;
+        }
+        ubeg.push_back((int64_t)ord.size());
+        const double total = (double)counter / 100.0;                                        // RM2Job.java:95
+        for (int32_t i = 0; i < TI; i++) iprob[i] = isum[i] > 0.0 ? isum[i] / total : 0.0;    // DoubleSumAndDividerReducer.java:44
+        auto find_user = [&](int32_t id) -> int64_t {
+            const auto it = std::lower_bound(uid.begin(), uid.end(), id);
+            return (it != uid.end() && *it == id) ? (int64_t)(it - uid.begin()) : -1;
+        };
+        // ---- expansion: one virtual cluster per listed user ----
+        std::vector<int32_t> xu, xi, vuser, vcluster, vsize((size_t)n_listed), owner_vid((size_t)n_listed), vreal;
+        std::vector<float> xs;
+        std::vector<double> vsum;
+        std::vector<int32_t> members;
+        int64_t next_vid = 1;
+        for (int64_t q = 0; q < n_listed; q++) {
+            members.clear();
+            members.push_back(user[q]);
+            for (int32_t t = 0; t < k; t++) { const int32_t v = neighbour[q * k + t]; if (v >= 0 && v != user[q]) members.push_back(v); }
+            std::sort(members.begin(), members.end());
+            members.erase(std::unique(members.begin(), members.end()), members.end());
+            vsize[q] = (int32_t)members.size();
+            for (const int32_t mreal : members) {
+                const int64_t ux = find_user(mreal);
+                if (ux < 0) return ctx->fail(FY_E_USER_WITHOUT_RATING, "user %d (listed, or a neighbour of user %d) has no positive rating", mreal, user[q]);
+                if (next_vid >= 0x7fffffff) return ctx->fail(FY_E_UNSUPPORTED, "too many (user, neighbour) pairs for one call: split the user list");
+                const int32_t vid = (int32_t)next_vid++;
+                if (mreal == user[q]) owner_vid[q] = vid;
+                vuser.push_back(vid); vcluster.push_back((int32_t)q); vreal.push_back(mreal); vsum.push_back(usum[ux]);
+                for (int64_t x = ubeg[ux]; x < ubeg[ux + 1]; x++) { xu.push_back(vid); xi.push_back(hi[ord[x]]); xs.push_back(hs[ord[x]]); }
+            }
+        }
+        if ((int64_t)xu.size() > 0x7fffffffll - 1024 || n_listed * (int64_t)TI > (1ll << 28))
+            return ctx->fail(FY_E_UNSUPPORTED, "neighbour-list job too large for one call (%lld expanded ratings, %lld listed users x %d item ids): split the user list",
+                             (long long)xu.size(), (long long)n_listed, TI);
+        // ---- child context: the ordinary pipeline on the groups, global statistics passed in, owners only ----
+        if (!ctx->nbr_child) {
+            fy_rm2_params kp = ctx->prm;
+            kp.filter_users = 0; kp.shard_rank = 0; kp.shard_count = 1; kp.n_gpus = 0;
+            const int rc = fy_rm2_create(&ctx->nbr_child, &kp);
+            if (rc != FY_OK) return ctx->fail(rc, "could not create the neighbour-list context");
+        }
+        fy_rm2_ctx* ch = ctx->nbr_child;
+        int rc = upload_ratings(ch, xu.data(), xi.data(), xs.data(), (int64_t)xu.size());
+        if (rc == FY_OK) rc = upload_clustering(ch, vuser.data(), vcluster.data(), (int64_t)vuser.size(), vsize.data(), (int32_t)n_listed, true);
+        if (rc != FY_OK) return ctx->fail(rc, "%s", ch->err);
+        const int32_t V = (int32_t)vuser.size();
+        std::vector<double> us_rank((size_t)V);
+        for (int32_t j = 0; j < V; j++) us_rank[ch->h_input_rank[j]] = vsum[j];
+        ch->owner_rank.assign((size_t)n_listed, 0);
+        std::vector<int32_t> rank_of_vid((size_t)V + 1, 0);
+        for (int32_t j = 0; j < V; j++) rank_of_vid[vuser[j]] = ch->h_input_rank[j];
+        for (int64_t q = 0; q < n_listed; q++) ch->owner_rank[q] = rank_of_vid[owner_vid[q]];
+        ch->ext_usum.need(V); ch->ext_iprob.need((size_t)ch->max_item + 1);
+        CK(cudaMemcpyAsync(ch->ext_usum.p, us_rank.data(), (size_t)V * 8, cudaMemcpyHostToDevice, ch->stream));
+        CK(cudaMemcpyAsync(ch->ext_iprob.p, iprob.data(), ((size_t)ch->max_item + 1) * 8, cudaMemcpyHostToDevice, ch->stream));
+        CK(cudaStreamSynchronize(ch->stream));
+        ch->use_ext = true; ch->split = 0; ch->n_splits = 1;
+        rc = run_pipeline(ch);
+        ch->use_ext = false;
+        ch->owner_rank.clear();
+        ch->have_ratings = false; ch->have_clustering = false;
+        if (rc != FY_OK) return ctx->fail(rc, "%s", ch->err);
+        // ---- virtual ids back to the callers' user ids (cluster = position of the user in the call) ----
+        if (ch->n_results > 0) {
+            std::vector<int32_t> pu((size_t)ch->n_results);
+            CK(cudaMemcpyAsync(pu.data(), ch->p_user.p, (size_t)ch->n_results * 4, cudaMemcpyDeviceToHost, ch->stream));
+            CK(cudaStreamSynchronize(ch->stream));
+            for (int32_t& v : pu) v = vreal[(size_t)v - 1];
+            CK(cudaMemcpyAsync(ch->p_user.p, pu.data(), (size_t)ch->n_results * 4, cudaMemcpyHostToDevice, ch->stream));
+        }
+        if (ch->n_result_rows > 0) {
+            std::vector<int32_t> ru((size_t)ch->n_result_rows);
+            CK(cudaMemcpyAsync(ru.data(), ch->row_user.p, (size_t)ch->n_result_rows * 4, cudaMemcpyDeviceToHost, ch->stream));
+            CK(cudaStreamSynchronize(ch->stream));
+            for (int32_t& v : ru) v = vreal[(size_t)v - 1];
+            CK(cudaMemcpyAsync(ch->row_user.p, ru.data(), (size_t)ch->n_result_rows * 4, cudaMemcpyHostToDevice, ch->stream));
+        }
+        CK(cudaStreamSynchronize(ch->stream));
+        ctx->view = ch;
+        return (int)FY_OK;
+    });
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -28,7 +28,7 @@ EXPORTS = [
     "fy_rm2_stats", "fy_rm2_result_count", "fy_rm2_users_scored", "fy_rm2_results", "fy_rm2_results_device", "fy_rm2_score_group",
     "fy_rm2_get_profile", "fy_cooc_counts", "fy_cooc_topk", "fy_knn_neighbours",
     "fy_rm2_result_row_count", "fy_rm2_result_rows", "fy_rm2_nccl_unique_id", "fy_rm2_comm_init", "fy_rm2_comm_destroy",
-    "fy_rm2_shard_bounds", "fy_rm2_probe_plane_read", "fy_rm2_user_count",
+    "fy_rm2_shard_bounds", "fy_rm2_probe_plane_read", "fy_rm2_user_count", "fy_rm2_run_neighbours",
 ]
 # include/filmyou_seqfile.h
 SEQ_EXPORTS = [
@@ -156,6 +156,7 @@ def load_library():
     L.fy_rm2_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
     L.fy_rm2_comm_destroy.argtypes = [vp]
     L.fy_rm2_shard_bounds.argtypes = [vp, i32p]
+    L.fy_rm2_run_neighbours.argtypes = [vp, i32p, i32p, C.c_int32, C.c_int64]
     L.fy_rm2_user_count.argtypes = [vp]
     L.fy_rm2_user_count.restype = C.c_int64
     L.fy_rm2_probe_plane_read.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, f64p, f64p]
@@ -359,6 +360,13 @@ class Rm2Engine:
             self._h, int(cluster_id), int(split), int(n_splits), _ptr(group_user, C.c_int32),
             _ptr(group_user_sum, C.c_double), len(group_user), _ptr(r_user, C.c_int32), _ptr(r_item, C.c_int32),
             _ptr(r_score, C.c_float), len(r_user), _ptr(item_prob, C.c_double), len(item_prob) - 1))
+
+    def run_neighbours(self, user, neighbour):
+        """Score `user[q]` over the explicit neighbour list `neighbour[q]` ([n, k] user ids, -1 = empty slot)."""
+        user = _i32(user)
+        neighbour = np.ascontiguousarray(neighbour, dtype=np.int32).reshape(len(user), -1)
+        self._check(self._L.fy_rm2_run_neighbours(self._h, _ptr(user, C.c_int32), _ptr(neighbour, C.c_int32),
+                                                   neighbour.shape[1], len(user)))
 
     def run_files(self, input_dir, clustering_dir, clustering_count_dir, number_of_clusters, output_dir, rm2_dir=None):
         """RM2Job.run at the file level (SequenceFiles in, SequenceFile / MapFile out)."""

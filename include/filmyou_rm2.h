@@ -156,6 +156,17 @@ int fy_rm2_comm_destroy(fy_rm2_ctx* ctx);
 /* user-rank boundaries of the shards of the last run: bounds[shard_count + 1] */
 int fy_rm2_shard_bounds(const fy_rm2_ctx* ctx, int32_t* bounds);
 
+/* ---- f3 / north_star part 1: scoring over explicit neighbour lists ------------------------------------------------
+ * buildRecommendations(..., int[] neighbours, ...) (M/rm/AbstractRM2Reducer.java:321-323,342-346) for caller-supplied
+ * lists, e.g. the output of fy_knn_neighbours: user[q] is scored exactly as the reducer would score it in a group made
+ * of user[q] and neighbour[q*k .. q*k+k) (-1 = empty slot): K = |N(u)| + 1, candidate items = what u or a neighbour
+ * rated, neighbour sum over N(u) in ascending user id, p(i|C) / user sums = the global statistics of the ratings given
+ * to fy_rm2_set_ratings (no clustering needed).  Results: fy_rm2_results / result_count / result_rows (users in the
+ * order given; `cluster` = position q of the user in the call).  The reference only ever passes "the cluster minus u"
+ * (:215-216): with that list this call reproduces fy_rm2_run; beyond it no reference counterpart exists.
+ * Cost grows with sum_q sum_{v in {u} + N(u)} n_v expanded ratings; FY_E_UNSUPPORTED asks for a smaller user list. */
+int fy_rm2_run_neighbours(fy_rm2_ctx* ctx, const int32_t* user, const int32_t* neighbour, int32_t k, int64_t n_listed);
+
 /* Fine seam: one reduce() group, exactly the records the reducer receives
  * (M/rm/AbstractRM2Reducer.java:149-174): n_group_users (user, userSum) records, then the group's
  * rating records; item_prob is rm2/itemColl indexed by item id (size max_item+1).

@@ -143,6 +143,20 @@ int orc_rm2_run(const orc_params* p,
                 const int32_t* cluster_size, int32_t n_clusters,
                 const int32_t* only_users, int64_t n_only,
                 orc_result** out) {
+    return orc_rm2_run_ext(p, r_user, r_item, r_score, nnz, cl_user, cl_cluster, n_users, cluster_size, n_clusters,
+                           only_users, n_only, NULL, -1, out);
+}
+
+/* The same job with p(i|C) supplied by the caller (ext_item_prob[0..ext_max_item], NULL = computed as RM2-2 does):
+ * what one reduce() call sees, where itemColl comes from the DistributedCache MapFile (AbstractRM2Reducer.java:281-303),
+ * not from the group's own ratings.  Used by the neighbour-list mode of rm2_oracle.py. */
+int orc_rm2_run_ext(const orc_params* p,
+                    const int32_t* r_user, const int32_t* r_item, const float* r_score, int64_t nnz,
+                    const int32_t* cl_user, const int32_t* cl_cluster, int64_t n_users,
+                    const int32_t* cluster_size, int32_t n_clusters,
+                    const int32_t* only_users, int64_t n_only,
+                    const double* ext_item_prob, int32_t ext_max_item,
+                    orc_result** out) {
     if (!p || !out || nnz < 0 || n_users <= 0 || n_clusters <= 0 || p->top_n < 0) return ORC_E_ARG;
     *out = NULL;
     int rc = ORC_OK;
@@ -215,6 +229,10 @@ int orc_rm2_run(const orc_params* p,
     if (!isum || !iprob) { rc = ORC_E_NOMEM; goto done; }
     for (int64_t e = 0; e < m; e++) isum[rt[e].item] += (double)rt[e].score;
     for (int32_t i = 0; i <= max_item; i++) iprob[i] = isum[i] / total; /* DoubleSumAndDividerReducer.java:44 */
+    if (ext_item_prob) {                                 /* itemColl handed in, as the reducer reads it from the cache file */
+        if (ext_max_item < max_item) { rc = ORC_E_ARG; goto done; }   /* "p(i|C) not found", :294-298 */
+        for (int32_t i = 0; i <= max_item; i++) iprob[i] = ext_item_prob[i];
+    }
 
     /* ---- which users are scored ---- */
     wanted = (char*)malloc((size_t)n_users);

@@ -81,6 +81,14 @@ int orc_rm2_run(const orc_params* p,
                 const int32_t* only_users, int64_t n_only,
                 orc_result** out);
 
+int orc_rm2_run_ext(const orc_params* p,
+                    const int32_t* r_user, const int32_t* r_item, const float* r_score, int64_t nnz,
+                    const int32_t* cl_user, const int32_t* cl_cluster, int64_t n_users,
+                    const int32_t* cluster_size, int32_t n_clusters,
+                    const int32_t* only_users, int64_t n_only,
+                    const double* ext_item_prob /* may be NULL */, int32_t ext_max_item,
+                    orc_result** out);
+
 int64_t orc_result_count(const orc_result* r);
 double orc_result_seconds(const orc_result* r); /* wall time of the per-user scoring loops only */
 int64_t orc_result_users_scored(const orc_result* r);

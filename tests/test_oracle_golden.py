@@ -148,3 +148,23 @@ def test_generator_is_deterministic_and_exact():
     assert a.nnz == datagen.SHAPES["small"][2]
     assert len(np.unique(a.user.astype(np.int64) * 100000 + a.item)) == a.nnz
     assert a.cluster_size.min() >= 2 and a.cluster_size.sum() == a.n_users
+
+
+def test_neighbour_list_mode_reproduces_the_goldens_when_the_list_is_the_cluster(golden, golden_ratings):
+    # the oracle's neighbour mode (the `int[] neighbours` signature, AbstractRM2Reducer.java:321-323) is pinned by the
+    # reference's own data: with N(u) = cluster(u) minus u it must give the 507 golden triples, and bit for bit what the
+    # cluster mode gives (same K, same item universe, same ascending neighbour order)
+    r = golden_ratings
+    k = int(max(golden["clusteringCount"])) - 1
+    nbr = -np.ones((r.n_users, k), np.int64)
+    for q, u in enumerate(r.cl_user):
+        mates = r.cl_user[(r.cl_cluster == r.cl_cluster[q]) & (r.cl_user != u)]
+        nbr[q, :len(mates)] = mates
+    out = orc.run_neighbours(r.user, r.item, r.score, r.cl_user, nbr, golden["lambda"], golden["numberOfItems"], 1000)
+    gold = {(int(u), int(i)): s for u, i, s in golden["recommendations"]}
+    assert len(out["user"]) == 507
+    for u, i, s in zip(out["user"], out["item"], out["score32"]):
+        assert abs(gold[(int(u), int(i))] - float(s)) <= golden["accuracy"]
+    ref = orc.run(r.user, r.item, r.score, r.cl_user, r.cl_cluster, r.cluster_size, golden["lambda"], golden["numberOfItems"], 1000)
+    key = lambda d: sorted(zip(d["user"].tolist(), d["item"].tolist(), d["score64"].tolist()))
+    assert key(out) == key(ref)
