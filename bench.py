@@ -35,9 +35,9 @@ TOP_N = 100           # BASELINE.json configs: "RM2 top-100"
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    ncu --set full capture (profiles/r01_ncu_traffic.json); None when no capture exists."""
+    ncu --set full capture (profiles/r02_ncu_traffic.json); None when no capture exists."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
             return float(json.load(f)[kernel]["dram_bytes_per_launch"])
     except Exception:
         return None

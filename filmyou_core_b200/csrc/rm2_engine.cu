@@ -595,6 +595,9 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     // Sharded index: with exact (dyadic) scores the global statistics need no sort, so each rank sorts and
     // indexes only the ratings of the clusters it touches (~1/N of them) instead of all of them.
     const int world = ctx->prm.shard_count, me = ctx->prm.shard_rank;
+    // share of a cluster's H build in its score work, for the work partition (partition_targets); FY_SHARD_BETA=0 = equal score work
+    const char* beta_env = std::getenv("FY_SHARD_BETA");
+    const double shard_beta = beta_env ? std::atof(beta_env) : 0.55;
     const bool exact_ok = ctx->exact_scores && U <= (1 << 22) && TI <= (1 << 22);     // <= 2^22 addends per sum (k_scan_ratings)
     const bool sharded_index = world > 1 && exact_ok && !ctx->use_ext;
     int32_t ub = 0, ue = U;
@@ -628,8 +631,8 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
             CK(cub::DeviceScan::InclusiveSum(ctx->cub_tmp.p, tmp, ctx->work.p, ctx->work_scan.p, U, st));
         }
         // this rank's user range and the rank range of the clusters it touches, computed on the device
-        LAUNCH(ctx, k_shard_bounds, 1, std::max(32, ((world + 1 + 31) / 32) * 32), 0, ctx->work_scan.p, U, world, me,
-               ctx->rank_cluster.p, ctx->cstart.p, ctx->shard_dev.p);
+        LAUNCH(ctx, k_shard_bounds, 1, std::max(128, ((world + 1 + 31) / 32) * 32), 0, ctx->work_scan.p, U, world, me,
+               ctx->rank_cluster.p, ctx->cstart.p, KC, shard_beta, ctx->shard_dev.p);
         LAUNCH(ctx, k_compact_local, cdiv(nnz, 256), 256, 0, ctx->keys_a.p, ctx->in_score.p, nnz, item_bits,
                ctx->shard_dev.p + world + 1, ctx->keys_b.p, ctx->c_score.p, ctx->counters.p + 3);
         LAUNCH(ctx, k_item_prob_isum, cdiv(TI, 128), 128, 0, ctx->isum.p, TI, ctx->counters.p + 1, lambda,
@@ -759,9 +762,28 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
         // shard = contiguous range of user ranks with ~equal estimated work (n_u * I_c)
         if (world > 1) {
             const double tot = h_scan[U - 1];
+            std::vector<double> G((size_t)world + 1, 0.0);
+            const bool aware = KC <= MAX_PARTITION_CLUSTERS && world <= 64 && shard_beta > 0.0;
+            if (aware) {
+                std::vector<double> W((size_t)KC, 0.0);
+                for (int32_t c = 0; c < KC; c++) {
+                    const int32_t a = ctx->h_cstart[c], b = ctx->h_cstart[c + 1];
+                    W[c] = (b > a) ? h_scan[b - 1] - (a > 0 ? h_scan[a - 1] : 0.0) : 0.0;
+                }
+                partition_targets(W.data(), KC, shard_beta, world, G.data());
+            }
             for (int r = 1; r < world; r++) {
-                const double target = tot * (double)r / (double)world;
-                ctx->h_bounds[r] = (int32_t)(std::lower_bound(h_scan.begin(), h_scan.end(), target) - h_scan.begin());
+                const double target = aware ? G[r] : tot * (double)r / (double)world;
+                int32_t b = (int32_t)(std::lower_bound(h_scan.begin(), h_scan.end(), target) - h_scan.begin());
+                if (aware && b < U) {                     // snap to a cluster boundary the target equals up to rounding (k_shard_bounds)
+                    const double tol = 1e-9 * tot;
+                    const int32_t c = ctx->h_rank_cluster[b];
+                    const int32_t e0 = ctx->h_cstart[c], e1 = ctx->h_cstart[c + 1];
+                    const double p0 = e0 > 0 ? h_scan[e0 - 1] : 0.0, p1 = h_scan[e1 - 1];
+                    if (std::fabs(p0 - target) <= tol) b = e0;
+                    else if (std::fabs(p1 - target) <= tol) b = e1;
+                }
+                ctx->h_bounds[r] = std::max(ctx->h_bounds[r - 1], b);
             }
             ub = ctx->h_bounds[me]; ue = ctx->h_bounds[me + 1];
         }

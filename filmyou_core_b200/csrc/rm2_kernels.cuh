@@ -170,27 +170,92 @@ __global__ void k_item_prob_isum(const double* __restrict__ isum, int32_t table_
     if (s > 0.0) atomicMin(bmin_bits, (unsigned long long)__double_as_longlong(b > 0.0 ? b : 0.0));
 }
 
-// Shard boundaries on the device (no host round trip): shard r = user ranks [bounds[r], bounds[r+1]) holding ~1/world of
-// the estimated work sum n_u * I_c (lower_bound on the inclusive prefix sum -- integers below 2^53, so every rank gets the
-// same answer), then the rank range [rl, rh) of the clusters this rank touches.  out = bounds[world + 1], rl, rh.
+// Work partition over `world` ranks.  A rank pays the score work of its users (n_u * I_c per user, W[c] per whole cluster)
+// PLUS, once per cluster it touches, that cluster's H build (~ beta * W[c]: the build of a cluster costs about beta times
+// its score + top-N + re-score work at both benchmark shapes) -- the clusters that straddle a boundary are built twice,
+// so equal score work alone leaves the ranks with one more touched cluster ~10 % late (measured at 8 GPUs).  The minimal
+// maximum cost T is bisected with a greedy fill (contiguous ranges, monotone cost), G[r] = cumulative score work at
+// the end of rank r - 1.  Pure double arithmetic in a fixed order: device, host and the Python mirror agree.
+__host__ __device__ inline void partition_targets(const double* W, int n_clusters, double beta, int world, double* G /* [world + 1] */) {
+    double total = 0.0;
+    for (int c = 0; c < n_clusters; c++) total += W[c];
+    double lo = 0.0, hi = total * (1.0 + beta) + 1.0;
+    for (int it = 0; it < 64; it++) {
+        const double T = (it < 63) ? 0.5 * (lo + hi) : hi;          // the last pass fills G with the feasible bound
+        int c = 0;
+        while (c < n_clusters && !(W[c] > 0.0)) c++;
+        double rem = (c < n_clusters) ? W[c] : 0.0, pos = 0.0;
+        G[0] = 0.0;
+        for (int r = 0; r < world; r++) {
+            double budget = T;
+            while (c < n_clusters) {
+#ifdef __CUDA_ARCH__
+                const double fee = __dmul_rn(beta, W[c]);
+#else
+                const double fee = beta * W[c];
+#endif
+                if (!(budget > fee)) break;
+                budget -= fee;
+                const double take = rem < budget ? rem : budget;
+                rem -= take; budget -= take; pos += take;
+                if (rem > 0.0) break;
+                c++;
+                while (c < n_clusters && !(W[c] > 0.0)) c++;
+                rem = (c < n_clusters) ? W[c] : 0.0;
+            }
+            G[r + 1] = pos;
+        }
+        if (it < 63) { if (c >= n_clusters) hi = T; else lo = T; }
+    }
+    G[world] = total;
+}
+
+constexpr int MAX_PARTITION_CLUSTERS = 4096;      // beyond this (or world > 64) the plain equal-work rule is used
+
+// Shard boundaries on the device (no host round trip): shard r = user ranks [bounds[r], bounds[r+1]); then the rank
+// range [rl, rh) of the clusters this rank touches.  out = bounds[world + 1], rl, rh.  scan = inclusive prefix of the
+// per-user work (integers below 2^53, so every rank computes the same numbers).
 __global__ void k_shard_bounds(const double* __restrict__ scan, int32_t n_users, int32_t world, int32_t me,
-                               const int32_t* __restrict__ rank_cluster, const int32_t* __restrict__ cstart,
-                               int32_t* __restrict__ out) {
+                               const int32_t* __restrict__ rank_cluster, const int32_t* __restrict__ cstart, int32_t n_clusters,
+                               double beta, int32_t* __restrict__ out) {
+    __shared__ double s_W[MAX_PARTITION_CLUSTERS];
+    __shared__ double s_G[66];
+    const bool aware = n_clusters <= MAX_PARTITION_CLUSTERS && world <= 64 && beta > 0.0;
+    if (aware) {
+        for (int c = threadIdx.x; c < n_clusters; c += blockDim.x) {
+            const int32_t a = cstart[c], b = cstart[c + 1];
+            s_W[c] = (b > a) ? scan[b - 1] - (a > 0 ? scan[a - 1] : 0.0) : 0.0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) partition_targets(s_W, n_clusters, beta, world, s_G);
+        __syncthreads();
+    }
     const int r = threadIdx.x;
     if (r <= world) {
         int32_t b;
         if (r == 0) b = 0;
         else if (r >= world) b = n_users;
         else {
-            const double target = scan[n_users - 1] * (double)r / (double)world;
+            const double target = aware ? s_G[r] : scan[n_users - 1] * (double)r / (double)world;
             int32_t lo = 0, hi = n_users;
             while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (scan[mid] < target) lo = mid + 1; else hi = mid; }
             b = lo;
+            if (aware && b < n_users) {
+                // a target that is the end of a cluster (up to rounding) must fall ON the cluster boundary: one stray user
+                // on the wrong side would make a rank build a whole extra H
+                const double tol = 1e-9 * scan[n_users - 1];
+                const int32_t c = rank_cluster[b];
+                const int32_t e0 = cstart[c], e1 = cstart[c + 1];
+                const double p0 = e0 > 0 ? scan[e0 - 1] : 0.0, p1 = scan[e1 - 1];
+                if (fabs(p0 - target) <= tol) b = e0;
+                else if (fabs(p1 - target) <= tol) b = e1;
+            }
         }
         out[r] = b;
     }
     __syncthreads();
     if (r == 0) {
+        for (int q = 1; q <= world; q++) if (out[q] < out[q - 1]) out[q] = out[q - 1];       // monotone
         const int32_t ub = out[me], ue = out[me + 1];
         int32_t rl = 0, rh = 0;
         if (ue > ub) { rl = cstart[rank_cluster[ub]]; rh = cstart[rank_cluster[ue - 1] + 1]; }

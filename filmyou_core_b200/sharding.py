@@ -16,14 +16,76 @@ FIELDS = (("user", torch.int32), ("item", torch.int32), ("score64", torch.float6
           ("score32", torch.float32), ("cluster", torch.int32))
 
 
-def plan_shards(work, world):
-    """Boundaries [b_0=0, ..., b_world=len(work)] of contiguous ranges with ~equal total work;
-    same rule as run_pipeline() in csrc/rm2_engine.cu (lower_bound on the inclusive prefix sum)."""
+def partition_targets(W, beta, world):
+    """Cumulative score work at the end of each rank when a rank also pays beta * W[c] once per cluster it touches (the
+    H build of a straddled cluster is done by both neighbours): bisection of the minimal maximum cost with a greedy
+    fill.  Line for line the `partition_targets` of csrc/rm2_kernels.cuh (same double arithmetic, same order)."""
+    W = [float(x) for x in W]
+    n = len(W)
+    total = 0.0
+    for x in W:
+        total += x
+    lo, hi = 0.0, total * (1.0 + beta) + 1.0
+    G = [0.0] * (world + 1)
+    for it in range(64):
+        T = 0.5 * (lo + hi) if it < 63 else hi
+        c = 0
+        while c < n and not W[c] > 0.0:
+            c += 1
+        rem = W[c] if c < n else 0.0
+        pos = 0.0
+        G[0] = 0.0
+        for r in range(world):
+            budget = T
+            while c < n:
+                fee = beta * W[c]
+                if not budget > fee:
+                    break
+                budget -= fee
+                take = rem if rem < budget else budget
+                rem -= take; budget -= take; pos += take
+                if rem > 0.0:
+                    break
+                c += 1
+                while c < n and not W[c] > 0.0:
+                    c += 1
+                rem = W[c] if c < n else 0.0
+            G[r + 1] = pos
+        if it < 63:
+            if c >= n:
+                hi = T
+            else:
+                lo = T
+    G[world] = total
+    return G
+
+
+def plan_shards(work, world, cluster_start=None, beta=0.55):
+    """Boundaries [b_0=0, ..., b_world=len(work)] of contiguous ranges of the (cluster, user id)-ordered users.
+    With `cluster_start` (first rank of every cluster + the end) the rule is the engine's: equal cost where a rank pays
+    its users' work plus beta times the work of every cluster it touches (csrc/rm2_kernels.cuh k_shard_bounds); without
+    it (or beta = 0) equal work: lower_bound on the inclusive prefix sum."""
     scan = np.cumsum(np.asarray(work, dtype=np.float64))
     tot = scan[-1]
+    if cluster_start is not None and beta > 0.0:
+        cs = np.asarray(cluster_start, dtype=np.int64)
+        W = [float(scan[b - 1] - (scan[a - 1] if a > 0 else 0.0)) if b > a else 0.0 for a, b in zip(cs[:-1], cs[1:])]
+        targets = partition_targets(W, beta, world)
+    else:
+        targets = [tot * r / world for r in range(world + 1)]
     b = [0]
     for r in range(1, world):
-        b.append(int(np.searchsorted(scan, tot * r / world, side="left")))
+        x = int(np.searchsorted(scan, targets[r], side="left"))
+        if cluster_start is not None and beta > 0.0 and x < len(scan):
+            # a target that is the end of a cluster (up to rounding) falls ON the cluster boundary
+            c = int(np.searchsorted(cs, x, side="right") - 1)
+            e0, e1 = int(cs[c]), int(cs[c + 1])
+            p0, p1 = (scan[e0 - 1] if e0 > 0 else 0.0), scan[e1 - 1]
+            if abs(p0 - targets[r]) <= 1e-9 * tot:
+                x = e0
+            elif abs(p1 - targets[r]) <= 1e-9 * tot:
+                x = e1
+        b.append(max(b[-1], x))
     b.append(len(scan))
     return b
 

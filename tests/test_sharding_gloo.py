@@ -59,3 +59,30 @@ def test_plan_shards_balances_work_and_covers_everything():
         assert b[0] == 0 and b[-1] == len(work) and all(x <= y for x, y in zip(b, b[1:]))
         parts = [work[b[k]:b[k + 1]].sum() for k in range(world)]
         assert max(parts) <= work.sum() / world + work.max() + 1e-9
+
+
+def test_build_aware_partition_balances_cost_including_the_duplicated_builds():
+    # 50 clusters of roughly equal work over 8 ranks: with beta > 0 the rank that touches one more cluster gets less score
+    # work, so the maximum COST (work + beta * touched clusters' work) is lower than with the equal-work rule
+    rng = np.random.default_rng(1)
+    sizes = rng.integers(2500, 3000, 50)
+    cs = np.concatenate([[0], np.cumsum(sizes)])
+    work = rng.lognormal(0, 1, cs[-1]) * 1000
+    W = np.array([work[a:b].sum() for a, b in zip(cs[:-1], cs[1:])])
+
+    def max_cost(b, beta=0.55):
+        out = []
+        for k in range(len(b) - 1):
+            if b[k + 1] <= b[k]:
+                out.append(0.0); continue
+            c0 = np.searchsorted(cs, b[k], side="right") - 1
+            c1 = np.searchsorted(cs, b[k + 1] - 1, side="right") - 1
+            out.append(work[b[k]:b[k + 1]].sum() + beta * W[c0:c1 + 1].sum())
+        return max(out)
+    for world in (2, 4, 8):
+        plain = sharding.plan_shards(work, world)
+        aware = sharding.plan_shards(work, world, cluster_start=cs)
+        assert aware[0] == 0 and aware[-1] == len(work) and all(x <= y for x, y in zip(aware, aware[1:]))
+        assert max_cost(aware) <= max_cost(plain) + 2.0 * work.max()      # boundaries fall on whole users
+    assert max_cost(sharding.plan_shards(work, 8, cluster_start=cs)) < 0.98 * max_cost(sharding.plan_shards(work, 8))
+    assert sharding.plan_shards(work, 1, cluster_start=cs) == [0, len(work)]
