@@ -369,7 +369,8 @@ def main():
                          float(sum(p["score_launches"] for p in profs)), sum(p["ms_refine"] for p in profs),
                          float(profs[-1]["bytes_per_term"]), float(sum(p["exact_rerun"] for p in profs)),
                          float(profs[-1]["score_kernel"]), sum(p["ms_gather"] for p in profs),
-                         sum(p["gram_bytes"] for p in profs), float(sum(p["clusters_touched"] for p in profs))],
+                         sum(p["gram_bytes"] for p in profs), float(sum(p["clusters_touched"] for p in profs)),
+                         sum(p["ms_total"] for p in profs), float(eng.users_scored())],
                         dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -477,7 +478,7 @@ def main():
         per_rank.append({"ms_score": s[0], "score_bytes": s[1], "ms_gram": s[2], "ms_index": s[3], "ms_topn": s[4],
                          "launches": s[5], "score_launches": s[6], "ms_refine": s[7], "bytes_per_term": s[8],
                          "exact_rerun": s[9], "score_kernel": int(s[10]), "ms_gather": s[11], "gram_bytes": s[12],
-                         "clusters_touched": s[13]})
+                         "clusters_touched": s[13], "ms_total": s[14], "users": s[15]})
     worst = max(per_rank, key=lambda x: x["ms_score"])
     achieved = worst["score_bytes"] / (worst["ms_score"] * 1e-3) / 1e9 if worst["ms_score"] > 0 else 0.0
     hi = worst["bytes_per_term"] == 4.0
@@ -518,6 +519,10 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": workload, "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(sum(p["launches"] for p in per_rank)), "roofline": roofline,
             "users_scored": users, "datagen_s": t_gen, "result_digest": digest,
+            "per_rank_ms_per_step": [{"run": round(p["ms_total"] / args.steps, 3), "exchange_wait": round(p["ms_gather"] / args.steps, 3),
+                                      "index": round(p["ms_index"] / args.steps, 3), "build": round(p["ms_gram"] / args.steps, 3),
+                                      "score": round(p["ms_score"] / args.steps, 3), "clusters": p["clusters_touched"] / args.steps,
+                                      "users": int(p["users"])} for p in per_rank],
             "exchange": ("in-library NCCL exchange of the dense top-N blocks (fy_rm2_comm_init), inside the timed region: %.3f ms per step "
                          "on the slowest rank" % (max(p["ms_gather"] for p in per_rank) / args.steps)) if world > 1 else None}
     if world == 1 and not args.no_cpu_baseline:

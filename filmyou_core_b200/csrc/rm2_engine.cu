@@ -113,7 +113,8 @@ struct fy_rm2_ctx {
     DBuf<double> cand_score[2];
     DBuf<int> overflow;
     DBuf<uint64_t> perm_keys[2];
-    DBuf<int32_t> perm_vals, perm;
+    DBuf<int32_t> perm_vals, perm, row_perm, row_perm_vals;
+    DBuf<uint64_t> row_keys[2];
     DBuf<uint64_t> sort_keys[2];
     DBuf<int32_t> sort_idx[2], seg_off;
     DBuf<unsigned char> sort_tmp;
@@ -208,6 +209,16 @@ static int fan_out(fy_rm2_ctx* ctx, F&& f) {
 }
 
 extern "C" int fy_rm2_abi_version(void) { return FY_RM2_ABI_VERSION; }
+
+#ifdef FY_BOUNDS_CHECK
+// checked build only (tools/build_checked.py): device-side range violations counted since the library was loaded
+extern "C" long long fy_rm2_debug_violations(void) {
+    unsigned long long v = 0;
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(&v, fy::g_bounds_violations, sizeof(v)) != cudaSuccess) return -1;
+    return (long long)v;
+}
+#endif
 
 extern "C" void fy_rm2_default_params(fy_rm2_params* p) {
     if (!p) return;
@@ -810,6 +821,16 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
         LAUNCH(ctx, k_alpha_cuj, cdiv((int64_t)n_slots * 32, 256), 256, 0, ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, keys2, rank_bits,
                ctx->rank_cluster.p, ctx->cstart.p, ctx->csc_src.p, ctx->csc_delta.p, n_slots, ctx->c_alpha.p, ctx->csr_c.p,
                ctx->cbound.p);
+    // processing order of the H-build rows inside a cluster: most raters first
+    if (n_slots > 0) {
+        ctx->row_keys[0].need(ns1); ctx->row_keys[1].need(ns1); ctx->row_perm.need(ns1); ctx->row_perm_vals.need(ns1);
+        LAUNCH(ctx, k_row_perm_keys, cdiv(n_slots, 256), 256, 0, ctx->c_len.p, ctx->item_off.p, KC, n_slots, ctx->row_keys[0].p, ctx->row_perm_vals.p);
+        size_t tmp = 0;
+        const int end_bit = std::min(64, 32 + bits_for((uint64_t)KC));
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->row_keys[0].p, ctx->row_keys[1].p, ctx->row_perm_vals.p, ctx->row_perm.p, n_slots, 0, end_bit, st));
+        ctx->cub_tmp.need(tmp);
+        CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, ctx->row_keys[0].p, ctx->row_keys[1].p, ctx->row_perm_vals.p, ctx->row_perm.p, n_slots, 0, end_bit, st));
+    }
     // processing order of the score kernel inside a cluster: most active users first (LPT), so that the 60x-longer
     // CTA of a heavy user never starts at the tail of the grid
     {
@@ -926,6 +947,11 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     const char* h2_env = std::getenv("FY_H2_CFG");
     const int h2_cfg = h2_env ? std::atoi(h2_env) : 0;
     const char* h2_order_env = std::getenv("FY_H2_ORDER");
+    // most-raters-first row order: pays when a row walks many raters (Netflix shape, ~113 raters per row: 4.8 vs 6.5 ms per
+    // cluster), costs a little when rows are short and the write locality of the item order matters more (ML-20M shape, ~15
+    // raters per row: 2.76 vs 2.64 ms) -- decided by the average raters per row of this run; FY_H2_LPT=0/1 forces it
+    const char* h2_lpt_env = std::getenv("FY_H2_LPT");
+    const bool h2_lpt = h2_lpt_env ? std::strcmp(h2_lpt_env, "0") != 0 : ((double)m >= 48.0 * (double)std::max(n_slots, 1));
     const char* h2_bulk_env = std::getenv("FY_H2_BULK");
     const bool h2_bulk = !(h2_bulk_env && std::strcmp(h2_bulk_env, "0") == 0);
     int32_t h2_rw = 1536, h2_nw = 2;                 // measured best of the instances below at ML-20M and Netflix shape
@@ -960,7 +986,8 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
             const bool rowmaj = !(h2_order_env && std::strcmp(h2_order_env, "0") == 0);                              \
             LAUNCH_ON(ctx, strm, (k_build_H2<RW, NW, PM, BK>), rowmaj ? dim3((unsigned)I_c * (unsigned)nchunk) : dim3(I_c, nchunk), (NW) * 32, smem, I_c, ld, n_bound - 1, slot0,  \
                       ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, ctx->c_alpha.p, ctx->csc_lu.p, ctx->csc_delta.p, cp,  \
-                      ctx->csr_loc.p, ctx->csr_delta.p, Hp, Hhp, scale, rowmaj ? nchunk : 0);                         \
+                      ctx->csr_loc.p, ctx->csr_delta.p, Hp, Hhp, scale, rowmaj ? nchunk : 0,                          \
+                      h2_lpt ? ctx->row_perm.p : (const int32_t*)nullptr);                                            \
         } while (0)
 #define FY_H2_LAUNCH_PM(RW, NW, PM)                                                                                   \
         do { if (h2_bulk) FY_H2_LAUNCH_B(RW, NW, PM, true); else FY_H2_LAUNCH_B(RW, NW, PM, false); } while (0)

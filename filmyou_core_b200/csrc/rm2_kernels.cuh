@@ -22,6 +22,17 @@
 
 namespace fy {
 
+// -DFY_BOUNDS_CHECK: every index into a shared-memory accumulator, a candidate list, a staged row list or an output
+// block is range-checked on the device and counted (fy_rm2_debug_violations()).  compute-sanitizer is closed on the
+// development pool (profiles/r02_sanitizer_closed.txt), so the GPU suite is run once against a library built this way
+// (tools/build_checked.py); the product build compiles the checks out.
+#ifdef FY_BOUNDS_CHECK
+__device__ unsigned long long g_bounds_violations = 0ull;
+#define FY_CHECK(cond) do { if (!(cond)) atomicAdd(&fy::g_bounds_violations, 1ull); } while (0)
+#else
+#define FY_CHECK(cond) do { } while (0)
+#endif
+
 // error flags raised on the device, read back at the host sync points
 enum DevFlag : int {
     DF_UNKNOWN_USER = 0,
@@ -283,6 +294,7 @@ __global__ void k_compact_local(const uint64_t* __restrict__ keys, const float* 
     base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
     if (keep) {
         const unsigned long long pos = base + (unsigned long long)__popc(bal & ((1u << lane) - 1));
+        FY_CHECK(pos < (unsigned long long)nnz);
         keys_out[pos] = k;
         score_out[pos] = score[e];
     }
@@ -532,6 +544,7 @@ __global__ void k_delta(const uint64_t* __restrict__ keys, const float* __restri
     const double oml = __dsub_rn(1.0, lambda);
     const double q = __dmul_rn(oml, __ddiv_rn((double)s_score[e], usum[rank]));
     const double P = __dadd_rn(q, b);
+    FY_CHECK(item >= 0 && item < table_items && tloc[(size_t)c * table_items + item] >= 0);
     csr_loc[e] = tloc[(size_t)c * table_items + item];
     csr_delta[e] = __dsub_rn(P, b);
 }
@@ -599,6 +612,18 @@ __global__ void k_alpha_cuj(const int32_t* __restrict__ c_start, const int32_t* 
         }
         carry = __dadd_rn(carry, __shfl_sync(0xffffffffu, incl, 31));
     }
+}
+
+// sort key (cluster, most raters first) of every (cluster, item) slot -> processing order of the H-build rows: a popular
+// row walks thousands of raters one after the other and must not be the last one to start
+__global__ void k_row_perm_keys(const int32_t* __restrict__ c_len, const int32_t* __restrict__ item_off, int32_t n_clusters,
+                                int32_t n_slots, uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    int32_t lo = 0, hi = n_clusters;                         // cluster of the slot: last c with item_off[c] <= s
+    while (hi - lo > 1) { const int32_t mid = (lo + hi) >> 1; if (item_off[mid] <= s) lo = mid; else hi = mid; }
+    keys[s] = ((uint64_t)(uint32_t)lo << 32) | (uint64_t)(0xffffffffu - (uint32_t)c_len[s]);
+    vals[s] = s;
 }
 
 // sort key (cluster, most rated items first) of every user rank -> processing order of the score kernel
@@ -706,6 +731,7 @@ k_build_H(int32_t I_c, int32_t ld, int32_t n_slices, int32_t slot0,
             double val = 0.0;
             if (valid) {
                 col = csr_loc[e] - c0;
+                FY_CHECK(col >= 0 && col < w);
                 val = __dmul_rn(dr, csr_delta[e]);
             }
             const unsigned peers = __match_any_sync(0xffffffffu, col);
@@ -772,13 +798,15 @@ k_build_H2(int32_t I_c, int32_t ld, int32_t n_ranges, int32_t slot0,
            const int32_t* __restrict__ csc_lu, const double* __restrict__ csc_delta,
            const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ csr_loc,
            const double* __restrict__ csr_delta, double* __restrict__ H, uint32_t* __restrict__ Hh,
-           double plane_scale, int32_t nchunk /* CTAs per row; the grid is linear, row-major: the CTAs in flight write neighbouring memory */) {
+           double plane_scale, int32_t nchunk /* CTAs per row; the grid is linear, row-major: the CTAs in flight write neighbouring memory */,
+           const int32_t* __restrict__ row_perm /* slots of the cluster, most raters first (null = item order) */) {
     static_assert(RW % 128 == 0, "the write-out takes 128 columns per warp step");
     extern __shared__ __align__(16) unsigned char h2_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int32_t j, qb;
     if (nchunk > 0) { j = (int32_t)(blockIdx.x / (unsigned)nchunk); qb = (int32_t)(blockIdx.x % (unsigned)nchunk); }
     else { j = blockIdx.x; qb = blockIdx.y; }
+    if (row_perm) j = row_perm[slot0 + j] - slot0;
     const int32_t q = qb * NW + warp;
     if (q >= n_ranges) return;
     double* __restrict__ acc = reinterpret_cast<double*>(h2_smem) + (size_t)warp * RW;
@@ -841,6 +869,7 @@ k_build_H2(int32_t I_c, int32_t ld, int32_t n_ranges, int32_t slot0,
 #pragma unroll
             for (int z = 0; z < PF; z++) {
                 if (cnt[z] > 0) {
+                    FY_CHECK(lane >= cnt[z] || (col[z] >= c0 && col[z] < c0 + w));
                     if (lane < cnt[z]) accw[col[z]] = __dadd_rn(accb[col[z]], __dmul_rn(d[z], dl[z]));
                     if (cnt[z] > 32) {                                   // a heavy rater: its further entries, 4 gathers in flight
                         for (int32_t k = 32 + lane; k < cnt[z]; k += 128) {
@@ -854,7 +883,7 @@ k_build_H2(int32_t I_c, int32_t ld, int32_t n_ranges, int32_t slot0,
                             }
 #pragma unroll
                             for (int y = 0; y < 4; y++)
-                                if (c2[y] >= 0) accw[c2[y]] = __dadd_rn(accb[c2[y]], __dmul_rn(d[z], v2[y]));
+                                if (c2[y] >= 0) { FY_CHECK(c2[y] >= c0 && c2[y] < c0 + w); accw[c2[y]] = __dadd_rn(accb[c2[y]], __dmul_rn(d[z], v2[y])); }
                         }
                     }
                     __syncwarp();                                        // the next rater may hit columns other lanes just updated
@@ -1252,6 +1281,7 @@ k_score_f32(const uint32_t* __restrict__ Hf, int32_t I_c, int32_t ld, int32_t ra
         __syncthreads();
         for (int32_t k = threadIdx.x; k < cnt; k += SCORE_THREADS) {
             const int32_t j = csr_loc[e0 + base + k];
+            FY_CHECK(j >= 0 && j < I_c && k < SCORE_CHUNK);
             s_jc[k] = make_uint2((uint32_t)j, __float_as_uint((float)csr_c[e0 + base + k]));
             const int32_t d = j - tile0;
             if (d >= 0 && d < SCOREH_TILE) atomicOr(&s_rated[d >> 5], 1u << (d & 31));
@@ -1335,6 +1365,7 @@ k_refine_score(const double* __restrict__ H, int32_t ld, int32_t rank_begin, int
     const int32_t rank = rank_begin + blockIdx.x;
     const int32_t e0 = rowptr[rank], n = rowptr[rank + 1] - e0;
     const int32_t i = cand[(size_t)blockIdx.x * cap + q];
+    FY_CHECK(i >= 0 && q < cap);
     const double bi = c_b[slot0 + i];
     const double* __restrict__ Hi = H + i;
     double p = 1.0;
@@ -1398,6 +1429,7 @@ k_refine_sort(int32_t rank_begin, int32_t ub, int32_t slot0, const int32_t* __re
         }
     }
     for (int t = tid; t < n_out; t += REFINE_THREADS) {
+        FY_CHECK(t < P2 && t < out_stride && si[t] != 0x7fffffff);
         out_item[(size_t)orow * out_stride + t] = c_item[slot0 + si[t]];
         out_score[(size_t)orow * out_stride + t] = key_to_score(sk[t]);
     }
@@ -1532,6 +1564,7 @@ k_topn(const double* __restrict__ scores, const unsigned long long* __restrict__
         }
         if (take) {
             const int pos = atomicAdd(&s_nsel, 1);
+            FY_CHECK(pos < P2 && i < I_c);
             if (pos < P2) { sk[pos] = key; si[pos] = i; }
         }
     }
@@ -1553,6 +1586,7 @@ k_topn(const double* __restrict__ scores, const unsigned long long* __restrict__
         }
     }
     for (int t = tid; t < n_out; t += TOPN_THREADS) {
+        FY_CHECK(si[t] >= 0 && si[t] < I_c && t < out_stride);
         out_item[(size_t)orow * out_stride + t] = c_item[slot0 + si[t]];
         out_score[(size_t)orow * out_stride + t] = key_to_score(sk[t]);
     }
@@ -1715,6 +1749,7 @@ __global__ void k_pack(const int32_t* __restrict__ out_item, const double* __res
     const int32_t rank = rank_begin + r;
     const int32_t uid = rank_userid[rank], c = rank_cluster[rank];
     if (threadIdx.x == 0) { row_user[r] = uid; row_cluster[r] = c; }
+    FY_CHECK(n >= 0 && n <= out_stride && off >= 0 && off <= (int64_t)r * out_stride);
     for (int32_t t = threadIdx.x; t < n; t += blockDim.x) {
         const double s = out_score[(size_t)r * out_stride + t];
         p_user[off + t] = uid;

@@ -221,6 +221,11 @@ class Rm2Engine:
         if self._h:
             self._L.fy_rm2_destroy(self._h)
             self._h = C.c_void_p()
+            if hasattr(self._L, "fy_rm2_debug_violations"):           # a -DFY_BOUNDS_CHECK build (tools/build_checked.py)
+                self._L.fy_rm2_debug_violations.restype = C.c_longlong
+                v = self._L.fy_rm2_debug_violations()
+                if v != 0:
+                    raise Rm2Error(-7, "%d device-side bounds violations counted by the checked build" % v)
 
     def __del__(self):
         try:

@@ -386,6 +386,28 @@ def test_sharded_contexts_cover_all_users_once(dyadic):
     assert set(merged) == set(full) and all(np.array_equal(merged[u][0], full[u][0]) for u in full)
 
 
+@pytest.mark.parametrize("world", [3, 8])
+def test_shard_bounds_follow_the_documented_rule(world):
+    # the partition computed on the device (k_shard_bounds) = sharding.plan_shards, the Python statement of the rule:
+    # equal cost where a rank pays its users' n_u * I_c plus 0.55 x the work of every cluster it touches
+    from filmyou_core_b200 import sharding
+    r = datagen.generate("ml-100k")
+    order = np.lexsort((r.cl_user, r.cl_cluster))
+    n_u = np.bincount(r.user, minlength=r.n_users + 1)
+    cl_of = np.zeros(r.n_users + 1, np.int64); cl_of[r.cl_user] = r.cl_cluster
+    i_c = np.array([len(np.unique(r.item[cl_of[r.user] == c])) for c in range(r.n_clusters)])
+    work = n_u[r.cl_user[order]] * i_c[r.cl_cluster[order]]
+    cs = np.concatenate([[0], np.cumsum(r.cluster_size)])
+    want = sharding.plan_shards(work, world, cluster_start=cs)
+    for rank in (0, world - 1):
+        with fy.Rm2Engine(lam=0.1, number_of_items=r.n_items, top_n=10, shard_rank=rank, shard_count=world) as eng:
+            eng.set_ratings(r.user, r.item, r.score)
+            eng.set_clustering(r.cl_user, r.cl_cluster, r.cluster_size)
+            eng.run()
+            assert eng.shard_bounds().tolist() == want
+            assert eng.users_scored() == want[rank + 1] - want[rank]
+
+
 def test_size_independent_properties_ml100k():
     r = datagen.generate("ml-100k")
     out = gpu_run(r, 0.1, r.n_items, 100)
