@@ -164,7 +164,7 @@ def cpu_baseline(r, budget_s=20.0, seed=12345, n_sample=256):
         cal = run(one, s_cal, orc.MODE_LITERAL_FAST, cores)
         _CPU_CAL["rate"] = float(np.sum(inner_of(one))) / s_cal / max(cal["seconds"], 1e-3)
         light = one[:4]
-        s1 = max(1, int(np.ceil(float(np.sum(inner_of(light))) / 2.0e9)))
+        s1 = max(1, int(np.ceil(float(np.sum(inner_of(light))) / 4.0e8)))      # ~5 s of the strided row-major loop on one thread
         lit = run(light, s1, orc.MODE_LITERAL, 1)
         _CPU_CAL["literal_1thread_users_per_s"] = (float(np.sum(inner_of(light))) / s1 / max(lit["seconds"], 1e-3)) / mean_inner
         _CPU_CAL["literal_1thread_sample"] = "%d light users, every %d-th candidate, %.1f s" % (len(light), s1, lit["seconds"])

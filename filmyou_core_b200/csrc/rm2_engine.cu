@@ -911,6 +911,11 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
             if (lf >= 2 && std::abs(sexp) < 1000) plan[c] = Plan{2, lf >= 4 ? 4 : 2, sexp, std::ldexp(1.0, sexp)};
         }
     }
+    // k_score_f32_tma (rows staged by cp.async.bulk into a shared-memory ring) is kept as a measured alternative, OFF by
+    // default: 3.83 vs 3.38 ms per ML-20M cluster, 11.1 vs 8.0 ms per Netflix cluster -- every staged byte is used by exactly
+    // one thread, so the ring only adds a second trip through shared memory (2 x 43 GB at 128 B/clk/SM = 2.4 ms by itself)
+    const char* tma_env = std::getenv("FY_SCORE_TMA");
+    const bool score_tma = (tma_env && std::strcmp(tma_env, "1") == 0);
     const char* lpt_env = std::getenv("FY_SCORE_LPT");
     const bool lpt_on = !(lpt_env && std::strcmp(lpt_env, "0") == 0);
     ctx->prof.bytes_per_term = use_hi ? 4.0 : 8.0;
@@ -1090,7 +1095,16 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
             {
                 const size_t k = seg_begin(SEG_SCORE, sS);
                 if (use_hi) ctx->prof.score_kernel = std::max(ctx->prof.score_kernel, plan[c].mode);
-                if (use_hi && plan[c].mode == 2) {
+                if (use_hi && plan[c].mode == 2 && score_tma) {
+                    const dim3 g2(nb, ld / SCOREH_TILE);
+                    if (plan[c].lf >= 4) {
+                        CK(cudaFuncSetAttribute(k_score_f32_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_TMA_SMEM));
+                        LAUNCH_ON(ctx, sS, k_score_f32_tma<4>, g2, SCORE_TMA_THREADS, SCORE_TMA_SMEM, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, plan[c].scale, plan[c].sexp, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p, lpt);
+                    } else {
+                        CK(cudaFuncSetAttribute(k_score_f32_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_TMA_SMEM));
+                        LAUNCH_ON(ctx, sS, k_score_f32_tma<2>, g2, SCORE_TMA_THREADS, SCORE_TMA_SMEM, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, plan[c].scale, plan[c].sexp, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p, lpt);
+                    }
+                } else if (use_hi && plan[c].mode == 2) {
                     if (plan[c].lf >= 4)
                         LAUNCH_ON(ctx, sS, k_score_f32<4>, grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, plan[c].scale, plan[c].sexp, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p, lpt);
                     else

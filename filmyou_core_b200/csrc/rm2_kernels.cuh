@@ -185,39 +185,62 @@ __global__ void k_item_prob_isum(const double* __restrict__ isum, int32_t table_
 // PLUS, once per cluster it touches, that cluster's H build (~ beta * W[c]: the build of a cluster costs about beta times
 // its score + top-N + re-score work at both benchmark shapes) -- the clusters that straddle a boundary are built twice,
 // so equal score work alone leaves the ranks with one more touched cluster ~10 % late (measured at 8 GPUs).  The minimal
-// maximum cost T is bisected with a greedy fill (contiguous ranges, monotone cost), G[r] = cumulative score work at
-// the end of rank r - 1.  Pure double arithmetic in a fixed order: device, host and the Python mirror agree.
-__host__ __device__ inline void partition_targets(const double* W, int n_clusters, double beta, int world, double* G /* [world + 1] */) {
+// maximum cost T is found by a 33-section search (8 rounds of 32 probes) over a greedy fill (contiguous ranges, monotone
+// cost), G[r] = cumulative score work at the end of rank r - 1.  Pure double arithmetic in a fixed order with separately
+// rounded operations: device, host and the Python mirror agree.
+// greedy fill with budget T per rank: G[r + 1] = cumulative score work after rank r; true when everything is covered
+__host__ __device__ inline bool partition_fill(const double* W, int n_clusters, double beta, int world, double T, double* G) {
+    int c = 0;
+    while (c < n_clusters && !(W[c] > 0.0)) c++;
+    double rem = (c < n_clusters) ? W[c] : 0.0, pos = 0.0;
+    if (G) G[0] = 0.0;
+    for (int r = 0; r < world; r++) {
+        double budget = T;
+        while (c < n_clusters) {
+#ifdef __CUDA_ARCH__
+            const double fee = __dmul_rn(beta, W[c]);
+#else
+            const double fee = beta * W[c];
+#endif
+            if (!(budget > fee)) break;
+            budget -= fee;
+            const double take = rem < budget ? rem : budget;
+            rem -= take; budget -= take; pos += take;
+            if (rem > 0.0) break;
+            c++;
+            while (c < n_clusters && !(W[c] > 0.0)) c++;
+            rem = (c < n_clusters) ? W[c] : 0.0;
+        }
+        if (G) G[r + 1] = pos;
+    }
+    return c >= n_clusters;
+}
+// the l-th of 32 probe points strictly inside (lo, hi); separate roundings, so that device, host and Python agree
+__host__ __device__ inline double partition_probe(double lo, double hi, int l) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(lo, __ddiv_rn(__dmul_rn(__dsub_rn(hi, lo), (double)(l + 1)), 33.0));
+#else
+    const double w = hi - lo;
+    const double x = w * (double)(l + 1);
+    return lo + x / 33.0;
+#endif
+}
+constexpr int PARTITION_ROUNDS = 8;                  // 33^-8 = 7e-13 of the initial bracket
+
+// host form of the search (the device form below evaluates the 32 probes of a round on the 32 lanes of a warp)
+inline void partition_targets(const double* W, int n_clusters, double beta, int world, double* G /* [world + 1] */) {
     double total = 0.0;
     for (int c = 0; c < n_clusters; c++) total += W[c];
     double lo = 0.0, hi = total * (1.0 + beta) + 1.0;
-    for (int it = 0; it < 64; it++) {
-        const double T = (it < 63) ? 0.5 * (lo + hi) : hi;          // the last pass fills G with the feasible bound
-        int c = 0;
-        while (c < n_clusters && !(W[c] > 0.0)) c++;
-        double rem = (c < n_clusters) ? W[c] : 0.0, pos = 0.0;
-        G[0] = 0.0;
-        for (int r = 0; r < world; r++) {
-            double budget = T;
-            while (c < n_clusters) {
-#ifdef __CUDA_ARCH__
-                const double fee = __dmul_rn(beta, W[c]);
-#else
-                const double fee = beta * W[c];
-#endif
-                if (!(budget > fee)) break;
-                budget -= fee;
-                const double take = rem < budget ? rem : budget;
-                rem -= take; budget -= take; pos += take;
-                if (rem > 0.0) break;
-                c++;
-                while (c < n_clusters && !(W[c] > 0.0)) c++;
-                rem = (c < n_clusters) ? W[c] : 0.0;
-            }
-            G[r + 1] = pos;
-        }
-        if (it < 63) { if (c >= n_clusters) hi = T; else lo = T; }
+    for (int round = 0; round < PARTITION_ROUNDS; round++) {
+        int first = 32;
+        for (int l = 0; l < 32; l++)
+            if (partition_fill(W, n_clusters, beta, world, partition_probe(lo, hi, l), nullptr)) { first = l; break; }
+        const double nlo = first > 0 ? partition_probe(lo, hi, first - 1) : lo;
+        const double nhi = first < 32 ? partition_probe(lo, hi, first) : hi;
+        lo = nlo; hi = nhi;
     }
+    partition_fill(W, n_clusters, beta, world, hi, G);
     G[world] = total;
 }
 
@@ -238,7 +261,21 @@ __global__ void k_shard_bounds(const double* __restrict__ scan, int32_t n_users,
             s_W[c] = (b > a) ? scan[b - 1] - (a > 0 ? scan[a - 1] : 0.0) : 0.0;
         }
         __syncthreads();
-        if (threadIdx.x == 0) partition_targets(s_W, n_clusters, beta, world, s_G);
+        if (threadIdx.x < 32) {                                   // one warp: the 32 probes of a round on its 32 lanes
+            const int l = threadIdx.x;
+            double total = 0.0;
+            for (int c = 0; c < n_clusters; c++) total += s_W[c];
+            double lo = 0.0, hi = __dadd_rn(__dmul_rn(total, __dadd_rn(1.0, beta)), 1.0);
+            for (int round = 0; round < PARTITION_ROUNDS; round++) {
+                const bool ok = partition_fill(s_W, n_clusters, beta, world, partition_probe(lo, hi, l), nullptr);
+                const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                const int first = bal ? (__ffs(bal) - 1) : 32;
+                const double nlo = first > 0 ? partition_probe(lo, hi, first - 1) : lo;
+                const double nhi = first < 32 ? partition_probe(lo, hi, first) : hi;
+                lo = nlo; hi = nhi;
+            }
+            if (l == 0) { partition_fill(s_W, n_clusters, beta, world, hi, s_G); s_G[world] = total; }
+        }
         __syncthreads();
     }
     const int r = threadIdx.x;
@@ -1318,6 +1355,192 @@ k_score_f32(const uint32_t* __restrict__ Hf, int32_t I_c, int32_t ld, int32_t ra
     p[0] = __uint_as_float((uint32_t)p01); p[1] = __uint_as_float((uint32_t)(p01 >> 32));
     p[2] = __uint_as_float((uint32_t)p23); p[3] = __uint_as_float((uint32_t)(p23 >> 32));
     __syncthreads();
+    const double pvpi = __dsub_rn(__dmul_rn((double)(n - 1), log_items), __dmul_rn((double)n, log_K));
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double NANV = __longlong_as_double(0x7ff8000000000000ll);
+    double s[4];
+    const int d = 4 * threadIdx.x;
+    const unsigned word = s_rated[d >> 5];
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const double et = (double)(ex[q] - n * scale_exp);               // undo the 2^s on each of the n factors
+        s[q] = fma(et, LN2_HI, fma(et, LN2_LO, log((double)p[q]))) + pvpi;
+        if (((word >> ((d + q) & 31)) & 1u) || i + q >= I_c) s[q] = NANV;
+        if (s[q] == s[q]) { const unsigned long long k = desc_key(s[q]); kmin = min(kmin, k); kmax = max(kmax, k); cnt++; }
+    }
+    double* dst = scores + (size_t)bx * ld + i;
+    *reinterpret_cast<double2*>(dst) = make_double2(s[0], s[1]);
+    *reinterpret_cast<double2*>(dst + 2) = make_double2(s[2], s[3]);
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0) {
+        unsigned long long* st = ustat + 3 * (size_t)bx;
+        atomicAdd(st, (unsigned long long)cnt);
+        atomicMin(st + 1, kmin);
+        atomicMax(st + 2, kmax);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_score_f32_tma (round 2): the same arithmetic as k_score_f32, with the plane rows brought in by the bulk-copy engine.
+// The plane-read probe showed that the 16-byte __ldg version is latency bound, not L2 bound (3.4 ms against 2.1 ms for the
+// same loads without arithmetic): a warp alternates "issue 8 loads - wait - 110 instructions" and the other resident warps
+// do not cover the waits.  Here a row segment (512 candidates x 4 B = 2 KB, contiguous) is ONE cp.async.bulk into a
+// shared-memory ring of SCORE_TMA_STAGES stages x 8 rows, issued by a dedicated producer warp and tracked by full / empty
+// mbarriers; the four consumer warps only read shared memory (LDS.128) and do arithmetic, so the copies of the next two
+// stages are always in flight while a stage is consumed, and the per-row global-load and address instructions disappear.
+// MEASURED (one B200): slower than the __ldg kernel, 3.83 vs 3.38 ms per ML-20M-sized cluster and 11.1 vs 8.0 ms per
+// Netflix-sized one.  No byte of a row segment is shared between threads, so the ring is a second trip through shared
+// memory: 2 x 43 GB per cluster at 128 B/clk/SM is 2.4 ms before any arithmetic.  Bulk staging pays where a tile is
+// re-read by many threads (the GEMM operands), not for a stream that every thread reads once.  Kept behind
+// FY_SCORE_TMA=1 as the record of that experiment; the product path is k_score_f32.
+// ---------------------------------------------------------------------------------------------
+constexpr int SCORE_TMA_STAGES = 3;
+constexpr int SCORE_TMA_ROWS = 8;                      // rows per stage
+constexpr int SCORE_TMA_THREADS = SCORE_THREADS + 32;  // 4 consumer warps + 1 producer warp
+constexpr size_t SCORE_TMA_SMEM = (size_t)SCORE_TMA_STAGES * SCORE_TMA_ROWS * SCOREH_TILE * 4;
+
+__device__ __forceinline__ void mbar_init_s(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int LF>
+__global__ void __launch_bounds__(SCORE_TMA_THREADS)
+k_score_f32_tma(const uint32_t* __restrict__ Hf, int32_t I_c, int32_t ld, int32_t rank_begin, int32_t slot0,
+                const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_loc,
+                const double* __restrict__ csr_c, const double* __restrict__ c_b, double plane_scale, int32_t scale_exp,
+                double log_items, double log_K, double* __restrict__ scores, unsigned long long* __restrict__ ustat,
+                const int32_t* __restrict__ perm /* users of the batch, most active first (null = rank order) */) {
+    extern __shared__ __align__(128) unsigned char tma_ring[];           // [stages][rows][512] uint32
+    __shared__ uint2 s_jc[SCORE_CHUNK];                                  // (local row j, float bits of c(u,j))
+    __shared__ unsigned s_rated[SCOREH_TILE / 32];
+    __shared__ __align__(8) unsigned long long s_bar[2 * SCORE_TMA_STAGES];
+
+    const int32_t bx = perm ? perm[rank_begin + blockIdx.x] - rank_begin : (int32_t)blockIdx.x;
+    const int32_t rank = rank_begin + bx;
+    const int32_t tile0 = blockIdx.y * SCOREH_TILE;
+    const int32_t e0 = rowptr[rank];
+    const int32_t n = rowptr[rank + 1] - e0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool producer = (warp == SCORE_THREADS / 32);
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(tma_ring);
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(s_bar);
+    auto full = [&](int st) { return bars + 8u * (uint32_t)st; };
+    auto empty = [&](int st) { return bars + 8u * (uint32_t)(SCORE_TMA_STAGES + st); };
+
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < SCORE_TMA_STAGES; st++) { mbar_init_s(full(st), 1); mbar_init_s(empty(st), SCORE_THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < SCOREH_TILE / 32) s_rated[threadIdx.x] = 0u;
+
+    const int32_t i = tile0 + 4 * (int32_t)threadIdx.x;                  // consumers only (threadIdx.x < 128)
+    float b[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    int ex[4] = {0, 0, 0, 0};
+    if (!producer) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) b[q] = (i + q < I_c) ? (float)(c_b[slot0 + i + q] * plane_scale) : 0.0f;
+    }
+    const f32x2_t b01 = pack_f32x2(b[0], b[1]), b23 = pack_f32x2(b[2], b[3]);
+    f32x2_t p01 = pack_f32x2(1.0f, 1.0f), p23 = p01;
+    const uint32_t* __restrict__ Hrow = Hf + tile0;                      // + j * ld: the 2 KB segment of row j
+    uint32_t step = 0;                                                   // stage counter, runs across chunks (ring position / phase)
+
+    for (int32_t base = 0; base < n; base += SCORE_CHUNK) {
+        const int32_t cnt = min(SCORE_CHUNK, n - base);
+        __syncthreads();                                                 // everyone is done with the previous chunk's list
+        if (!producer) {
+            for (int32_t k = threadIdx.x; k < cnt; k += SCORE_THREADS) {
+                const int32_t j = csr_loc[e0 + base + k];
+                FY_CHECK(j >= 0 && j < I_c && k < SCORE_CHUNK);
+                s_jc[k] = make_uint2((uint32_t)j, __float_as_uint((float)csr_c[e0 + base + k]));
+                const int32_t d = j - tile0;
+                if (d >= 0 && d < SCOREH_TILE) atomicOr(&s_rated[d >> 5], 1u << (d & 31));
+            }
+        }
+        __syncthreads();
+        const int32_t n_stage = (cnt + SCORE_TMA_ROWS - 1) / SCORE_TMA_ROWS;
+        if (producer) {
+            // lanes 0..7 each copy one row of the stage; lane 0 registers the stage's byte count first
+            for (int32_t sg = 0; sg < n_stage; sg++) {
+                const uint32_t it = step + (uint32_t)sg;
+                const int st = (int)(it % SCORE_TMA_STAGES);
+                const uint32_t ph = (it / SCORE_TMA_STAGES) & 1u;
+                const int32_t rows = min(SCORE_TMA_ROWS, cnt - sg * SCORE_TMA_ROWS);
+                if (lane == 0) {
+                    mbar_wait_s(empty(st), ph ^ 1u);                     // the four consumer warps have left this stage
+                    mbar_expect_tx_s(full(st), (uint32_t)rows * SCOREH_TILE * 4u);
+                }
+                __syncwarp();
+                if (lane < rows) {
+                    const uint32_t j = s_jc[sg * SCORE_TMA_ROWS + lane].x;
+                    bulk_g2s(ring + (uint32_t)((st * SCORE_TMA_ROWS + lane) * SCOREH_TILE * 4), Hrow + (size_t)j * ld, SCOREH_TILE * 4u, full(st));
+                }
+            }
+        } else {
+            for (int32_t sg = 0; sg < n_stage; sg++) {
+                const uint32_t it = step + (uint32_t)sg;
+                const int st = (int)(it % SCORE_TMA_STAGES);
+                const uint32_t ph = (it / SCORE_TMA_STAGES) & 1u;
+                const int32_t rows = min(SCORE_TMA_ROWS, cnt - sg * SCORE_TMA_ROWS);
+                mbar_wait_s(full(st), ph);
+                const uint4* __restrict__ rowbase = reinterpret_cast<const uint4*>(tma_ring) + (size_t)(st * SCORE_TMA_ROWS) * (SCOREH_TILE / 4) + threadIdx.x;
+                const uint2* __restrict__ jc = s_jc + sg * SCORE_TMA_ROWS;
+                if (rows == SCORE_TMA_ROWS) {
+#pragma unroll
+                    for (int q = 0; q < SCORE_TMA_ROWS; q++) {
+                        const uint4 h = rowbase[q * (SCOREH_TILE / 4)];
+                        const uint32_t cb = jc[q].y;
+                        const f32x2_t c2 = pack_u32x2(cb, cb);
+                        p01 = fmul2(p01, ffma2(b01, c2, pack_u32x2(h.x, h.y)));
+                        p23 = fmul2(p23, ffma2(b23, c2, pack_u32x2(h.z, h.w)));
+                        if ((q + 1) % LF == 0) { peel_exponent_f2(p01, ex[0], ex[1]); peel_exponent_f2(p23, ex[2], ex[3]); }
+                    }
+                } else {
+                    for (int q = 0; q < rows; q++) {
+                        const uint4 h = rowbase[q * (SCOREH_TILE / 4)];
+                        const uint32_t cb = jc[q].y;
+                        const f32x2_t c2 = pack_u32x2(cb, cb);
+                        p01 = fmul2(p01, ffma2(b01, c2, pack_u32x2(h.x, h.y)));
+                        p23 = fmul2(p23, ffma2(b23, c2, pack_u32x2(h.z, h.w)));
+                        if ((q + 1) % LF == 0 || q + 1 == rows) { peel_exponent_f2(p01, ex[0], ex[1]); peel_exponent_f2(p23, ex[2], ex[3]); }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_s(empty(st));                 // this warp has read the stage
+            }
+        }
+        step += (uint32_t)n_stage;
+    }
+    __syncthreads();
+    if (producer) return;
+    float p[4];
+    p[0] = __uint_as_float((uint32_t)p01); p[1] = __uint_as_float((uint32_t)(p01 >> 32));
+    p[2] = __uint_as_float((uint32_t)p23); p[3] = __uint_as_float((uint32_t)(p23 >> 32));
     const double pvpi = __dsub_rn(__dmul_rn((double)(n - 1), log_items), __dmul_rn((double)n, log_K));
     const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
     const double NANV = __longlong_as_double(0x7ff8000000000000ll);

@@ -16,46 +16,62 @@ FIELDS = (("user", torch.int32), ("item", torch.int32), ("score64", torch.float6
           ("score32", torch.float32), ("cluster", torch.int32))
 
 
+def _partition_fill(W, beta, world, T, G=None):
+    n = len(W)
+    c = 0
+    while c < n and not W[c] > 0.0:
+        c += 1
+    rem = W[c] if c < n else 0.0
+    pos = 0.0
+    if G is not None:
+        G[0] = 0.0
+    for r in range(world):
+        budget = T
+        while c < n:
+            fee = beta * W[c]
+            if not budget > fee:
+                break
+            budget -= fee
+            take = rem if rem < budget else budget
+            rem -= take; budget -= take; pos += take
+            if rem > 0.0:
+                break
+            c += 1
+            while c < n and not W[c] > 0.0:
+                c += 1
+            rem = W[c] if c < n else 0.0
+        if G is not None:
+            G[r + 1] = pos
+    return c >= n
+
+
+def _partition_probe(lo, hi, l):
+    w = hi - lo
+    x = w * float(l + 1)
+    return lo + x / 33.0
+
+
 def partition_targets(W, beta, world):
     """Cumulative score work at the end of each rank when a rank also pays beta * W[c] once per cluster it touches (the
-    H build of a straddled cluster is done by both neighbours): bisection of the minimal maximum cost with a greedy
-    fill.  Line for line the `partition_targets` of csrc/rm2_kernels.cuh (same double arithmetic, same order)."""
+    H build of a straddled cluster is done by both neighbours): 33-section search (8 rounds of 32 probes) of the minimal
+    maximum cost over a greedy fill.  Line for line the `partition_targets` / `k_shard_bounds` of csrc/rm2_kernels.cuh
+    (same double arithmetic, every operation rounded separately)."""
     W = [float(x) for x in W]
-    n = len(W)
     total = 0.0
     for x in W:
         total += x
     lo, hi = 0.0, total * (1.0 + beta) + 1.0
+    for _ in range(8):
+        first = 32
+        for l in range(32):
+            if _partition_fill(W, beta, world, _partition_probe(lo, hi, l)):
+                first = l
+                break
+        nlo = _partition_probe(lo, hi, first - 1) if first > 0 else lo
+        nhi = _partition_probe(lo, hi, first) if first < 32 else hi
+        lo, hi = nlo, nhi
     G = [0.0] * (world + 1)
-    for it in range(64):
-        T = 0.5 * (lo + hi) if it < 63 else hi
-        c = 0
-        while c < n and not W[c] > 0.0:
-            c += 1
-        rem = W[c] if c < n else 0.0
-        pos = 0.0
-        G[0] = 0.0
-        for r in range(world):
-            budget = T
-            while c < n:
-                fee = beta * W[c]
-                if not budget > fee:
-                    break
-                budget -= fee
-                take = rem if rem < budget else budget
-                rem -= take; budget -= take; pos += take
-                if rem > 0.0:
-                    break
-                c += 1
-                while c < n and not W[c] > 0.0:
-                    c += 1
-                rem = W[c] if c < n else 0.0
-            G[r + 1] = pos
-        if it < 63:
-            if c >= n:
-                hi = T
-            else:
-                lo = T
+    _partition_fill(W, beta, world, hi, G)
     G[world] = total
     return G
 
