@@ -442,6 +442,7 @@ extern "C" int fy_rm2_set_clustering(fy_rm2_ctx* ctx, const int32_t* user, const
     if (!ctx) return FY_E_ARG;
     if (!user || !cluster || !cluster_size || n_users <= 0 || n_clusters <= 0)
         return ctx->fail(FY_E_ARG, "fy_rm2_set_clustering: null pointer or empty input");
+    ctx->view = nullptr;
     if (!ctx->kids.empty()) {
         ctx->have_results = false;
         ctx->n_users = (int32_t)n_users;

@@ -72,3 +72,20 @@ def test_product_package_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(d, f)).read()
                 assert "oracle" not in txt.lower() or f == "__init__.py" and False, os.path.join(d, f)
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    # the ctypes mirrors of fy_rm2_params / fy_rm2_profile (and what a Panama struct layout would declare) against the C header
+    import ctypes
+    import subprocess
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "filmyou_rm2.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %d\\n", sizeof(fy_rm2_params), offsetof(fy_rm2_params, n_gpus), '
+                   'sizeof(fy_rm2_profile), offsetof(fy_rm2_profile, ms_gather), offsetof(fy_rm2_profile, score_kernel), FY_RM2_ABI_VERSION); return 0; }\n')
+    exe = str(tmp_path / "sizes")
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe])
+    sp, on, sf, og, ok, ver = (int(x) for x in subprocess.check_output([exe], text=True).split())
+    assert ctypes.sizeof(fy.Rm2Params) == sp == 48 and fy.Rm2Params.n_gpus.offset == on
+    from filmyou_core_b200.engine import Rm2Profile
+    assert ctypes.sizeof(Rm2Profile) == sf and Rm2Profile.ms_gather.offset == og and Rm2Profile.score_kernel.offset == ok
+    assert ver == 3
