@@ -15,6 +15,9 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 struct orc_result {
     int64_t count;
@@ -85,6 +88,77 @@ static int cmp_i32(const void* a, const void* b) {
     int32_t x = *(const int32_t*)a, y = *(const int32_t*)b;
     return x < y ? -1 : (x > y ? 1 : 0);
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * GRAM mode only: G = P^T P for the columns [i0, i1) against every column j >= i0 (upper triangle, mirrored), P stored
+ * transposed (column i = K contiguous doubles).  The 32 columns of an i-block stay in the core's L2 while the j columns
+ * stream past once; a 4 x 2 register block of AVX2 accumulators (separate multiply and add: no FMA, like the rest of this
+ * file) does the dot products.  The summation order is (v mod 4) partial sums -- GRAM is the algebra cross-check of the
+ * reducer's loop, not a restatement of its order (the LITERAL modes are).
+ * ------------------------------------------------------------------------------------------- */
+static void gram_block_scalar(const double* P, int64_t K, int64_t I, double* G, int64_t i0, int64_t i1) {
+    for (int64_t i = i0; i < i1; i++)
+        for (int64_t j = i; j < I; j++) {
+            const double* a = P + (size_t)i * (size_t)K;
+            const double* b = P + (size_t)j * (size_t)K;
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            int64_t v = 0;
+            for (; v + 4 <= K; v += 4) {
+                s0 += a[v] * b[v]; s1 += a[v + 1] * b[v + 1];
+                s2 += a[v + 2] * b[v + 2]; s3 += a[v + 3] * b[v + 3];
+            }
+            for (; v < K; v++) s0 += a[v] * b[v];
+            const double s = (s0 + s1) + (s2 + s3);
+            G[(size_t)i * (size_t)I + (size_t)j] = s;
+            G[(size_t)j * (size_t)I + (size_t)i] = s;
+        }
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2")))
+static double hsum4(__m256d x, double tail) {
+    double t[4];
+    _mm256_storeu_pd(t, x);
+    return ((t[0] + tail) + t[1]) + (t[2] + t[3]);
+}
+
+__attribute__((target("avx2")))
+static void gram_block_avx2(const double* P, int64_t K, int64_t I, double* G, int64_t i0, int64_t i1) {
+    for (int64_t j = i0; j < I; j += 2) {
+        const int nj = (j + 1 < I) ? 2 : 1;
+        const double* b0 = P + (size_t)j * (size_t)K;
+        const double* b1 = P + (size_t)(j + nj - 1) * (size_t)K;
+        for (int64_t ii = i0; ii < i1 && ii <= j + nj - 1; ii += 4) {
+            const int ni = (int)((i1 - ii) < 4 ? (i1 - ii) : 4);
+            const double* a[4];
+            for (int q = 0; q < 4; q++) a[q] = P + (size_t)(ii + (q < ni ? q : ni - 1)) * (size_t)K;
+            __m256d c00 = _mm256_setzero_pd(), c01 = c00, c10 = c00, c11 = c00, c20 = c00, c21 = c00, c30 = c00, c31 = c00;
+            int64_t v = 0;
+            for (; v + 4 <= K; v += 4) {
+                const __m256d x0 = _mm256_loadu_pd(b0 + v), x1 = _mm256_loadu_pd(b1 + v);
+                const __m256d y0 = _mm256_loadu_pd(a[0] + v), y1 = _mm256_loadu_pd(a[1] + v);
+                const __m256d y2 = _mm256_loadu_pd(a[2] + v), y3 = _mm256_loadu_pd(a[3] + v);
+                c00 = _mm256_add_pd(c00, _mm256_mul_pd(y0, x0)); c01 = _mm256_add_pd(c01, _mm256_mul_pd(y0, x1));
+                c10 = _mm256_add_pd(c10, _mm256_mul_pd(y1, x0)); c11 = _mm256_add_pd(c11, _mm256_mul_pd(y1, x1));
+                c20 = _mm256_add_pd(c20, _mm256_mul_pd(y2, x0)); c21 = _mm256_add_pd(c21, _mm256_mul_pd(y2, x1));
+                c30 = _mm256_add_pd(c30, _mm256_mul_pd(y3, x0)); c31 = _mm256_add_pd(c31, _mm256_mul_pd(y3, x1));
+            }
+            double t[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+            for (; v < K; v++)
+                for (int q = 0; q < 4; q++) { t[q][0] += a[q][v] * b0[v]; t[q][1] += a[q][v] * b1[v]; }
+            const double r[4][2] = {{hsum4(c00, t[0][0]), hsum4(c01, t[0][1])}, {hsum4(c10, t[1][0]), hsum4(c11, t[1][1])},
+                                    {hsum4(c20, t[2][0]), hsum4(c21, t[2][1])}, {hsum4(c30, t[3][0]), hsum4(c31, t[3][1])}};
+            for (int q = 0; q < ni; q++)
+                for (int w = 0; w < nj; w++) {
+                    const int64_t i = ii + q, jj = j + w;
+                    if (i > jj) continue;
+                    G[(size_t)i * (size_t)I + (size_t)jj] = r[q][w];
+                    G[(size_t)jj * (size_t)I + (size_t)i] = r[q][w];
+                }
+        }
+    }
+}
+#endif
 
 /* ---------------------------------------------------------------------------------------------
  * Statistics: jobs RM2-1 (userSum + truncated total) and RM2-2 (p(i|C)).
@@ -317,24 +391,23 @@ int orc_rm2_run_ext(const orc_params* p,
         if (p->mode == ORC_MODE_GRAM) {
             G = (double*)malloc(sizeof(double) * (size_t)I * (size_t)I);
             if (!G) { free(P); free(items); free(loc); rc = ORC_E_NOMEM; break; }
-#pragma omp parallel for schedule(dynamic, 4)
-            for (int64_t i = 0; i < I; i++)
-                for (int64_t j = i; j < I; j++) {
-                    /* four partial sums (v mod 4), combined at the end: GRAM is the algebra cross-check,
-                     * its order is not the reducer's (LITERAL* keep the reducer's order) */
-                    const double* a = P + (size_t)i * (size_t)K;
-                    const double* b = P + (size_t)j * (size_t)K;
-                    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-                    int64_t v = 0;
-                    for (; v + 4 <= K; v += 4) {
-                        s0 += a[v] * b[v]; s1 += a[v + 1] * b[v + 1];
-                        s2 += a[v + 2] * b[v + 2]; s3 += a[v + 3] * b[v + 3];
-                    }
-                    for (; v < K; v++) s0 += a[v] * b[v];
-                    const double s = (s0 + s1) + (s2 + s3);
-                    G[(size_t)i * (size_t)I + (size_t)j] = s;
-                    G[(size_t)j * (size_t)I + (size_t)i] = s;
+            {
+                int use_avx2 = 0;
+#if defined(__x86_64__)
+                use_avx2 = __builtin_cpu_supports("avx2");
+#endif
+                const int64_t IB = 32;                         /* columns of an i-block: 32 x K doubles stay in L2 */
+                const int64_t n_blocks = (I + IB - 1) / IB;
+#pragma omp parallel for schedule(dynamic, 1)
+                for (int64_t bk = 0; bk < n_blocks; bk++) {
+                    const int64_t i0 = bk * IB, i1 = (i0 + IB < I) ? i0 + IB : I;
+#if defined(__x86_64__)
+                    if (use_avx2) { gram_block_avx2(P, K, I, G, i0, i1); continue; }
+#endif
+                    gram_block_scalar(P, K, I, G, i0, i1);
                 }
+                (void)use_avx2;
+            }
         }
 
         /* per-user result slots so that the parallel loop is deterministic */
