@@ -827,6 +827,14 @@ k_build_H(int32_t I_c, int32_t ld, int32_t n_slices, int32_t slot0,
 // The write-out handles 4 columns per lane per step and is specialised on the plane mode.
 // Summation order per accumulator = ascending rater, separate multiply and add: identical to k_build_H.
 // ---------------------------------------------------------------------------------------------
+// Two light raters per step (lanes 0-15 / 16-31, one match_any to order a shared column): bit-identical, measured SLOWER
+// (2.92 vs 2.64 ms per ML-20M-sized cluster, 5.73 vs 4.85 ms Netflix-sized) -- the kernel is not bound by its step count.
+// Compiled out; -DFY_H2_PAIR=1 brings the experiment back.
+#ifndef FY_H2_PAIR
+#define FY_H2_PAIR 0
+#endif
+constexpr bool H2_PAIR = FY_H2_PAIR != 0;
+
 template <int RW, int NW, int PM /* 0 = fp64 plane only, 1 = + hi words, 2 = + float(H * plane_scale) */, bool BULK /* write-out by cp.async.bulk */>
 __global__ void __launch_bounds__(NW * 32)
 k_build_H2(int32_t I_c, int32_t ld, int32_t n_ranges, int32_t slot0,
@@ -885,27 +893,63 @@ k_build_H2(int32_t I_c, int32_t ld, int32_t n_ranges, int32_t slot0,
         // vice versa, so PF..2*PF gathers are in flight per warp (the single-step look-ahead was latency bound:
         // 25 % of the stall samples sat on the first use of the gathered column).
         constexpr int PF = 4;
-        int32_t loA[PF], cntA[PF], colA[PF], loB[PF], cntB[PF], colB[PF];
+        int32_t loA[PF], cntA[PF], cn2A[PF], colA[PF], loB[PF], cntB[PF], cn2B[PF], colB[PF];
         double dA[PF], dlA[PF], dB[PF], dlB[PF];
-        auto fetch = [&](int32_t (&lo)[PF], int32_t (&cnt)[PF], int32_t (&col)[PF], double (&d)[PF], double (&dl)[PF]) {
+        // A slot holds one rater (lanes = its first 32 entries) or, when two consecutive raters have <= 16 entries each in this
+        // range (the common case at ML-20M shape: 12 of 32 lanes were busy per step), BOTH: lanes 0-15 the earlier rater,
+        // lanes 16-31 the later one (cn2 > 0).  The earlier rater's update of a column both touch is applied first.
+        auto fetch = [&](int32_t (&lo)[PF], int32_t (&cnt)[PF], int32_t (&cn2)[PF], int32_t (&col)[PF], double (&d)[PF], double (&dl)[PF]) {
 #pragma unroll
             for (int z = 0; z < PF; z++) {
-                cnt[z] = 0; lo[z] = 0; col[z] = c0; d[z] = 0.0; dl[z] = 0.0;
+                cnt[z] = 0; cn2[z] = 0; lo[z] = 0; col[z] = c0; d[z] = 0.0; dl[z] = 0.0;
                 if (m) {
                     const int r = __ffs(m) - 1;
                     m &= m - 1;
-                    lo[z] = __shfl_sync(0xffffffffu, lo_l, r);
-                    cnt[z] = __shfl_sync(0xffffffffu, cnt_l, r);
-                    d[z] = __shfl_sync(0xffffffffu, d_l, r);
-                    if (lane < cnt[z]) { col[z] = csr_loc[lo[z] + lane]; dl[z] = csr_delta[lo[z] + lane]; }
+                    const int32_t lo1 = __shfl_sync(0xffffffffu, lo_l, r);
+                    const int32_t c1 = __shfl_sync(0xffffffffu, cnt_l, r);
+                    const double d1 = __shfl_sync(0xffffffffu, d_l, r);
+                    int32_t lo2 = 0, c2 = 0;
+                    double d2 = 0.0;
+                    if (H2_PAIR && c1 <= 16 && m) {
+                        const int r2 = __ffs(m) - 1;
+                        const int32_t cc = __shfl_sync(0xffffffffu, cnt_l, r2);
+                        if (cc <= 16) {
+                            m &= m - 1;
+                            c2 = cc;
+                            lo2 = __shfl_sync(0xffffffffu, lo_l, r2);
+                            d2 = __shfl_sync(0xffffffffu, d_l, r2);
+                        }
+                    }
+                    lo[z] = lo1; cnt[z] = c1; cn2[z] = c2;
+                    if (c2 > 0) {
+                        const bool hi = lane >= 16;
+                        const int l16 = lane & 15;
+                        const int32_t mylo = hi ? lo2 : lo1, mycnt = hi ? c2 : c1;
+                        d[z] = hi ? d2 : d1;
+                        if (l16 < mycnt) { col[z] = csr_loc[mylo + l16]; dl[z] = csr_delta[mylo + l16]; }
+                    } else {
+                        d[z] = d1;
+                        if (lane < c1) { col[z] = csr_loc[lo1 + lane]; dl[z] = csr_delta[lo1 + lane]; }
+                    }
                 }
             }
         };
-        auto consume = [&](const int32_t (&lo)[PF], const int32_t (&cnt)[PF], const int32_t (&col)[PF], const double (&d)[PF],
-                           const double (&dl)[PF]) {
+        auto consume = [&](const int32_t (&lo)[PF], const int32_t (&cnt)[PF], const int32_t (&cn2)[PF], const int32_t (&col)[PF],
+                           const double (&d)[PF], const double (&dl)[PF]) {
 #pragma unroll
             for (int z = 0; z < PF; z++) {
-                if (cnt[z] > 0) {
+                if (cn2[z] > 0) {                                        // two raters in one step
+                    const bool valid = (lane & 15) < ((lane >= 16) ? cn2[z] : cnt[z]);
+                    FY_CHECK(!valid || (col[z] >= c0 && col[z] < c0 + w));
+                    const unsigned peers = __match_any_sync(0xffffffffu, valid ? col[z] : (-1 - lane));
+                    const bool first = (peers & ((1u << lane) - 1u)) == 0u;  // the earlier rater's lane (or the only one) of this column
+                    if (valid && first) accw[col[z]] = __dadd_rn(accb[col[z]], __dmul_rn(d[z], dl[z]));
+                    __syncwarp();
+                    if (__any_sync(0xffffffffu, valid && !first)) {
+                        if (valid && !first) accw[col[z]] = __dadd_rn(accb[col[z]], __dmul_rn(d[z], dl[z]));
+                        __syncwarp();
+                    }
+                } else if (cnt[z] > 0) {
                     FY_CHECK(lane >= cnt[z] || (col[z] >= c0 && col[z] < c0 + w));
                     if (lane < cnt[z]) accw[col[z]] = __dadd_rn(accb[col[z]], __dmul_rn(d[z], dl[z]));
                     if (cnt[z] > 32) {                                   // a heavy rater: its further entries, 4 gathers in flight
@@ -927,13 +971,13 @@ k_build_H2(int32_t I_c, int32_t ld, int32_t n_ranges, int32_t slot0,
                 }
             }
         };
-        fetch(loA, cntA, colA, dA, dlA);
+        fetch(loA, cntA, cn2A, colA, dA, dlA);
         for (;;) {
-            fetch(loB, cntB, colB, dB, dlB);
-            consume(loA, cntA, colA, dA, dlA);
+            fetch(loB, cntB, cn2B, colB, dB, dlB);
+            consume(loA, cntA, cn2A, colA, dA, dlA);
             if (cntB[0] == 0) break;
-            fetch(loA, cntA, colA, dA, dlA);
-            consume(loB, cntB, colB, dB, dlB);
+            fetch(loA, cntA, cn2A, colA, dA, dlA);
+            consume(loB, cntB, cn2B, colB, dB, dlB);
             if (cntA[0] == 0) break;
         }
     }
