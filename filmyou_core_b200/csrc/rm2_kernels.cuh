@@ -833,6 +833,10 @@ k_build_H(int32_t I_c, int32_t ld, int32_t n_slices, int32_t slot0,
 #ifndef FY_H2_PAIR
 #define FY_H2_PAIR 0
 #endif
+#ifndef FY_H2_FLOAT_DIRECT
+#define FY_H2_FLOAT_DIRECT 1
+#endif
+constexpr bool H2_FLOAT_DIRECT = FY_H2_FLOAT_DIRECT != 0;   // bulk write-out: 4-byte plane by ordinary stores in the finishing pass
 constexpr bool H2_PAIR = FY_H2_PAIR != 0;
 
 template <int RW, int NW, int PM /* 0 = fp64 plane only, 1 = + hi words, 2 = + float(H * plane_scale) */, bool BULK /* write-out by cp.async.bulk */>
@@ -998,6 +1002,15 @@ k_build_H2(int32_t I_c, int32_t ld, int32_t n_ranges, int32_t slot0,
             a.x = (t < w) ? __fma_rn(bj, __ldg(al + t), a.x) : 1.0;
             a.y = (t + 1 < w) ? __fma_rn(bj, __ldg(al + t + 1), a.y) : 1.0;
             *reinterpret_cast<double2*>(acc + t) = a;
+            if (PM != 0 && H2_FLOAT_DIRECT) {
+                // the 4-byte plane leaves in the same pass with ordinary 8-byte stores (a third of the bytes): converting it in
+                // place for a second bulk copy costs another read and write of the accumulator row in shared memory
+                uint2 o = (PM == 2)
+                    ? make_uint2(__float_as_uint((float)(a.x * plane_scale)), __float_as_uint((float)(a.y * plane_scale)))
+                    : make_uint2(hi_word_rn(a.x), hi_word_rn(a.y));
+                if (PM == 2 && t >= w) o = make_uint2(0x3f800000u, 0x3f800000u);     // padding columns: 1.0f, as k_build_H
+                *reinterpret_cast<uint2*>(rowh + t) = o;
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncwarp();
@@ -1006,7 +1019,7 @@ k_build_H2(int32_t I_c, int32_t ld, int32_t n_ranges, int32_t slot0,
                          :: "l"(row), "r"((unsigned)__cvta_generic_to_shared(acc)), "r"((unsigned)wp * 8u) : "memory");
             asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
         }
-        if (PM != 0) {
+        if (PM != 0 && !H2_FLOAT_DIRECT) {
             // 4-byte plane: converted in place, front to back (step s reads bytes [512 s, 512 s + 512) and writes
             // [256 s, 256 s + 256), which every earlier step has already consumed), after the fp64 copy has read the row
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
