@@ -958,11 +958,14 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     // raters per row: 2.76 vs 2.64 ms) -- decided by the average raters per row of this run; FY_H2_LPT=0/1 forces it
     const char* h2_lpt_env = std::getenv("FY_H2_LPT");
     const bool h2_lpt = h2_lpt_env ? std::strcmp(h2_lpt_env, "0") != 0 : ((double)m >= 48.0 * (double)std::max(n_slots, 1));
+    const char* h2_pad_env = std::getenv("FY_H2_PAD");               // experiment: extra dynamic shared memory per CTA (fewer resident CTAs)
+    const size_t h2_pad = h2_pad_env ? (size_t)std::atoi(h2_pad_env) : 0;
     const char* h2_bulk_env = std::getenv("FY_H2_BULK");
     const bool h2_bulk = !(h2_bulk_env && std::strcmp(h2_bulk_env, "0") == 0);
     // Default 1536 x 2: alone, 1024-column ranges are a little faster (2.50 vs 2.56 ms per ML-20M cluster), but inside the job their
     // extra resident warps slow the score kernel running beside them -- 342.5 vs 320.1 ms per ML-20M job, same box, twice
-    int32_t h2_rw = 1536, h2_nw = 2;
+    // (one warp per CTA is 1 % better again than two: 313.3 / 316.5 vs 316.9-320 ms on two boxes)
+    int32_t h2_rw = 1536, h2_nw = 1;
     switch (h2_cfg) {
         case 1: h2_rw = 2048; h2_nw = 2; break;
         case 2: h2_rw = 512; h2_nw = 8; break;
@@ -971,7 +974,7 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
         case 5: h2_rw = 1024; h2_nw = 2; break;
         case 6: h2_rw = 1280; h2_nw = 2; break;
         case 7: h2_rw = 768; h2_nw = 2; break;
-        case 8: h2_rw = 1536; h2_nw = 1; break;
+        case 8: h2_rw = 1536; h2_nw = 2; break;
         default: break;
     }
     auto h_geometry = [&](int32_t I_c, int32_t& ld, int32_t& slice_w, int32_t& chunk_w, int32_t& nchunk, int32_t& n_bound) {
@@ -992,7 +995,7 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
                             const int32_t* cp, double* Hp, uint32_t* Hhp, int mode, double scale) {
 #define FY_H2_LAUNCH_B(RW, NW, PM, BK)                                                                                \
         do {                                                                                                          \
-            const size_t smem = (size_t)(NW) * (RW) * 8;                                                              \
+            const size_t smem = (size_t)(NW) * (RW) * 8 + h2_pad;                                                     \
             CK(cudaFuncSetAttribute(k_build_H2<RW, NW, PM, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             const bool rowmaj = !(h2_order_env && std::strcmp(h2_order_env, "0") == 0);                              \
             LAUNCH_ON(ctx, strm, (k_build_H2<RW, NW, PM, BK>), rowmaj ? dim3((unsigned)I_c * (unsigned)nchunk) : dim3(I_c, nchunk), (NW) * 32, smem, I_c, ld, n_bound - 1, slot0,  \
@@ -1017,8 +1020,8 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
                 case 5: FY_H2_LAUNCH(1024, 2); break;
                 case 6: FY_H2_LAUNCH(1280, 2); break;
                 case 7: FY_H2_LAUNCH(768, 2); break;
-                case 8: FY_H2_LAUNCH(1536, 1); break;
-                default: FY_H2_LAUNCH(1536, 2); break;
+                case 8: FY_H2_LAUNCH(1536, 2); break;
+                default: FY_H2_LAUNCH(1536, 1); break;
             }
             return;
         }
