@@ -917,6 +917,11 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     // one thread, so the ring only adds a second trip through shared memory (2 x 43 GB at 128 B/clk/SM = 2.4 ms by itself)
     const char* tma_env = std::getenv("FY_SCORE_TMA");
     const bool score_tma = (tma_env && std::strcmp(tma_env, "1") == 0);
+    const char* spad_env = std::getenv("FY_SCORE_PAD");              // experiment: dynamic shared memory per score CTA (fewer resident CTAs)
+    const size_t score_pad = spad_env ? (size_t)std::atoi(spad_env) : 0;
+    if (score_pad > 40 * 1024) CK(cudaFuncSetAttribute(k_score_f32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score_pad));
+    const char* minb_env = std::getenv("FY_SCORE_MINB");
+    const int score_minb = minb_env ? std::atoi(minb_env) : 0;
     const char* lpt_env = std::getenv("FY_SCORE_LPT");
     const bool lpt_on = !(lpt_env && std::strcmp(lpt_env, "0") == 0);
     ctx->prof.bytes_per_term = use_hi ? 4.0 : 8.0;
@@ -1116,9 +1121,14 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
                         CK(cudaFuncSetAttribute(k_score_f32_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_TMA_SMEM));
                         LAUNCH_ON(ctx, sS, k_score_f32_tma<2>, g2, SCORE_TMA_THREADS, SCORE_TMA_SMEM, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, plan[c].scale, plan[c].sexp, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p, lpt);
                     }
+                } else if (use_hi && plan[c].mode == 2 && score_minb > 1 && plan[c].lf >= 4) {
+                    // experiment (FY_SCORE_MINB): the same kernel compiled for a minimum residency of 6 / 10 / 12 CTAs per SM
+#define FY_SCORE_MB(MB) LAUNCH_ON(ctx, sS, (k_score_f32<4, MB>), grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, plan[c].scale, plan[c].sexp, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p, lpt)
+                    if (score_minb >= 12) FY_SCORE_MB(12); else if (score_minb >= 10) FY_SCORE_MB(10); else FY_SCORE_MB(6);
+#undef FY_SCORE_MB
                 } else if (use_hi && plan[c].mode == 2) {
                     if (plan[c].lf >= 4)
-                        LAUNCH_ON(ctx, sS, k_score_f32<4>, grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, plan[c].scale, plan[c].sexp, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p, lpt);
+                        LAUNCH_ON(ctx, sS, k_score_f32<4>, grid, SCORE_THREADS, score_pad, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, plan[c].scale, plan[c].sexp, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p, lpt);
                     else
                         LAUNCH_ON(ctx, sS, k_score_f32<2>, grid, SCORE_THREADS, 0, ctx->Hh[hb].p, I_c, ld, b0, slot0, ctx->rowptr.p, ctx->csr_loc.p, ctx->csr_c.p, ctx->c_b.p, plan[c].scale, plan[c].sexp, log_items, log_K, ctx->scores[sb].p, ctx->ustat[sb].p, lpt);
                 } else if (use_hi) {

@@ -1343,8 +1343,8 @@ __device__ __forceinline__ void peel_exponent_f2(f32x2_t& p, int& e0, int& e1) {
     p = pack_u32x2(lo, hi);
 }
 
-template <int LF>
-__global__ void __launch_bounds__(SCORE_THREADS)
+template <int LF, int MINB = 1>
+__global__ void __launch_bounds__(SCORE_THREADS, MINB)
 k_score_f32(const uint32_t* __restrict__ Hf, int32_t I_c, int32_t ld, int32_t rank_begin, int32_t slot0,
             const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_loc,
             const double* __restrict__ csr_c, const double* __restrict__ c_b, double plane_scale, int32_t scale_exp,
