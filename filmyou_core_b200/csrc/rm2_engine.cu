@@ -1,12 +1,16 @@
 // rm2_engine.cu -- host side of libfilmyou_rm2.so: context, C ABI (include/filmyou_rm2.h) and the
 // stream-ordered pipeline that replaces jobs RM2-1..3 of M/rm/RM2Job.java:76-100.
 //
-// Pipeline of fy_rm2_run (everything on one CUDA stream, two host sync points for sizes):
+// Pipeline of fy_rm2_run (index phase on the context's stream, then three streams; host sync points: A for input
+// errors and sizes, B / B2 for the per-cluster plan, C1 / C2 at the end):
 //   index : ratings -> (user rank, item) sort -> CSR; (item, user rank) sort -> CSC; user sums,
-//           truncated total, p(i|C); per-cluster local item numbering; d, alpha, c(u,j)
-//   per cluster of this shard:  k_build_H  ->  k_score<L>  ->  k_topn
-//   pack  : dense [user x N] results -> packed triples
-// cub::DeviceRadixSort / DeviceScan are used for the two plumbing sorts and two scans only; every
+//           truncated total, p(i|C); per-cluster local item numbering; d, alpha, c(u,j); with shard_count > 1 and exact
+//           (dyadic) scores each rank indexes only the ratings of the clusters it touches
+//   per cluster of this shard:  stream G: k_build_H2 (cluster c+1)  |  stream S: k_score_f32 (cluster c)  |
+//                               stream T: k_topn + k_refine_score + k_refine_sort (cluster c-1); H and scores double buffered
+//   exchange (communicator attached): grouped in-place ncclBroadcast of every rank's [rows x N] block
+//   pack  : dense [user x N] results -> packed triples + one (user, cluster, count) record per row
+// cub::DeviceRadixSort / DeviceScan / DeviceSegmentedSort are used for the plumbing sorts and scans only; every
 // kernel on the scoring path is in rm2_kernels.cuh.
 #include "../../include/filmyou_rm2.h"
 #include "rm2_kernels.cuh"
@@ -196,13 +200,16 @@ template <class F>
 static int fan_out(fy_rm2_ctx* ctx, F&& f) {
     const size_t n = ctx->kids.size();
     std::vector<int> rc(n, FY_OK);
+    std::vector<std::thread> th;
+    bool started_all = true;
     try {
-        std::vector<std::thread> th;
+        th.reserve(n);
         for (size_t i = 0; i < n; i++) th.emplace_back([&, i]() { rc[i] = f(ctx->kids[i], i); });
-        for (std::thread& t : th) t.join();
     } catch (...) {
-        return ctx->fail(FY_E_NOMEM, "could not start a host thread per device");
+        started_all = false;           // join what did start before reporting: a joinable std::thread must not be destroyed
     }
+    for (std::thread& t : th) t.join();
+    if (!started_all) return ctx->fail(FY_E_NOMEM, "could not start a host thread per device");
     for (size_t i = 0; i < n; i++)
         if (rc[i] != FY_OK) return ctx->fail(rc[i], "device %d: %s", ctx->kids[i]->prm.device, ctx->kids[i]->err);
     return FY_OK;

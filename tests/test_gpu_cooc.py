@@ -55,9 +55,9 @@ def test_knn_neighbours_match_integer_restatement(shape):
     # a9 / f3: no reference symbol exists; the check is numpy's exact integer B B^T + (count desc, id asc) top-k
     r = datagen.generate(shape)
     n_u, n_i, k = r.n_users + 1, r.n_items + 1, 20
-    B = np.zeros((n_u, n_i), np.int32)
+    B = np.zeros((n_u, n_i), np.float64)
     B[r.user, r.item] = 1
-    Cuu = B @ B.T
+    Cuu = (B @ B.T).astype(np.int32)            # BLAS on 0/1 doubles: every partial sum is an integer < 2^53, exact
     rows = np.arange(n_u) if n_u <= 1000 else np.random.default_rng(1).choice(n_u, 600, replace=False)
     wi, wc, wn = _topk_ref(Cuu, k, rows)
     with fy.Rm2Engine(number_of_items=r.n_items) as eng:
