@@ -958,7 +958,8 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     auto seg_begin = [&](int kind, cudaStream_t strm) { CK(cudaEventRecord(ctx->ev(evi), strm)); segs.push_back(Seg{kind, evi, 0}); evi++; return segs.size() - 1; };
     auto seg_end = [&](size_t k, cudaStream_t strm) { CK(cudaEventRecord(ctx->ev(evi), strm)); segs[k].e1 = evi; evi++; };
     const size_t SCORE_BUF_BYTES = big_n ? ((size_t)1 << 29) : ((size_t)2 << 30);
-    // H-build variant: 2 (default) = k_build_H2 (warp per (row, wide column range), rater-sequential, cp.async ring);
+    // H-build variant: 2 (default) = k_build_H2 (warp per (row, wide column range), rater-sequential, batches of four raters
+    // prefetched in registers, fp64 plane written out by cp.async.bulk);
     // 1 = the round-1 flattened-list kernel (kept for A/B: FY_BUILD_H=1).  FY_H2_CFG picks the (range, warps, depth) instance.
     const char* bh_env = std::getenv("FY_BUILD_H");
     const int build_variant = (bh_env && std::strcmp(bh_env, "1") == 0) ? 1 : 2;
@@ -974,7 +975,7 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     const size_t h2_pad = h2_pad_env ? (size_t)std::atoi(h2_pad_env) : 0;
     const char* h2_bulk_env = std::getenv("FY_H2_BULK");
     const bool h2_bulk = !(h2_bulk_env && std::strcmp(h2_bulk_env, "0") == 0);
-    // Default 1536 x 2: alone, 1024-column ranges are a little faster (2.50 vs 2.56 ms per ML-20M cluster), but inside the job their
+    // Default 1536 columns x 1 warp per CTA: alone, 1024-column ranges are a little faster (2.50 vs 2.56 ms per ML-20M cluster), but inside the job their
     // extra resident warps slow the score kernel running beside them -- 342.5 vs 320.1 ms per ML-20M job, same box, twice
     // (one warp per CTA is 1 % better again than two: 313.3 / 316.5 vs 316.9-320 ms on two boxes)
     int32_t h2_rw = 1536, h2_nw = 1;
