@@ -111,8 +111,8 @@ struct fy_rm2_ctx {
     double h_total = 0.0;
 
     // ---- per cluster ----
-    DBuf<double> H[2], scores[2];
-    DBuf<uint32_t> Hh[2];
+    DBuf<double> H[3], scores[2];           // H: two buffers (FY_H_BUFS=3: three, an experiment)
+    DBuf<uint32_t> Hh[3];
     DBuf<int32_t> cand[2], cand_cnt[2];
     DBuf<double> cand_score[2];
     DBuf<int> overflow;
@@ -123,9 +123,9 @@ struct fy_rm2_ctx {
     DBuf<int32_t> sort_idx[2], seg_off;
     DBuf<unsigned char> sort_tmp;
     DBuf<unsigned long long> cbound;
-    DBuf<int32_t> chunk_ptr2[2];
+    DBuf<int32_t> chunk_ptr2[3];
     cudaStream_t stream_g = nullptr, stream_t = nullptr;   // H build / top-N run beside the score stream
-    cudaEvent_t sync_ev[10] = {nullptr};
+    cudaEvent_t sync_ev[12] = {nullptr};
 
     // ---- results ----
     int32_t shard_begin = 0, shard_end = 0, out_stride = 0;
@@ -944,11 +944,13 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
     if (!ctx->stream_t) CK(cudaStreamCreateWithFlags(&ctx->stream_t, cudaStreamNonBlocking));
     for (cudaEvent_t& e : ctx->sync_ev) if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     cudaStream_t sS = st, sG = ctx->stream_g, sT = ctx->stream_t;
-    cudaEvent_t* hReady = ctx->sync_ev;       // [2] H[b] built
-    cudaEvent_t* hFree = ctx->sync_ev + 2;    // [2] last score kernel reading H[b] finished
-    cudaEvent_t* sReady = ctx->sync_ev + 4;   // [2] scores[b] written
-    cudaEvent_t* sFree = ctx->sync_ev + 6;    // [2] top-N finished reading scores[b]
-    cudaEvent_t evFork = ctx->sync_ev[8], evJoin = ctx->sync_ev[9];
+    cudaEvent_t* hReady = ctx->sync_ev;       // [3] H[b] built
+    cudaEvent_t* hFree = ctx->sync_ev + 3;    // [3] last kernel reading H[b] (score, or the exact re-score) finished
+    cudaEvent_t* sReady = ctx->sync_ev + 6;   // [2] scores[b] written
+    cudaEvent_t* sFree = ctx->sync_ev + 8;    // [2] top-N finished reading scores[b]
+    cudaEvent_t evFork = ctx->sync_ev[10], evJoin = ctx->sync_ev[11];
+    const char* hbufs_env = std::getenv("FY_H_BUFS");
+    const int n_hbuf = (hbufs_env && std::atoi(hbufs_env) == 3) ? 3 : 2;
     CK(cudaEventRecord(evFork, st));
     CK(cudaStreamWaitEvent(sG, evFork, 0));
     CK(cudaStreamWaitEvent(sT, evFork, 0));
@@ -1047,6 +1049,7 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
                   ctx->c_start.p, ctx->c_len.p, ctx->c_b.p, ctx->c_alpha.p, ctx->csc_lu.p, ctx->csc_delta.p,
                   cp, ctx->csr_loc.p, ctx->csr_delta.p, Hp, Hhp, mode, scale);
     };
+    int n_touched_total = 0;
     {   // size the per-cluster buffers once (growing them inside the loop would synchronise the device)
         size_t need_h = 0, need_cp = 0, need_sc = 0, need_us = 0;
         int n_touched = 0, n_batches = 0;
@@ -1065,20 +1068,25 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
             need_us = std::max(need_us, batch * 3);
             n_touched++; n_batches += cdiv(r1 - r0, (int64_t)batch);
         }
-        for (int b = 0; b < 2; b++) {
-            if (b == 1 && n_touched < 2) need_h = need_cp = 0;     // a single cluster needs one H
-            if (b == 1 && n_batches < 2) need_sc = need_us = 0;
-            ctx->H[b].need(need_h); ctx->chunk_ptr2[b].need(need_cp); ctx->scores[b].need(need_sc); ctx->ustat[b].need(need_us);
+        n_touched_total = n_touched;
+        for (int b = 0; b < 3; b++) {
+            const bool h_on = b == 0 || (b < n_hbuf && n_touched > b);          // a single cluster needs one H
+            const bool s_on = b == 0 || (b == 1 && n_batches >= 2);
+            if (h_on) { ctx->H[b].need(need_h); ctx->chunk_ptr2[b].need(need_cp); if (use_hi) ctx->Hh[b].need(need_h); }
+            if (s_on) {
+                ctx->scores[b].need(need_sc); ctx->ustat[b].need(need_us);
+                if (use_hi) { ctx->cand[b].need(need_us / 3 * cap); ctx->cand_score[b].need(need_us / 3 * cap); ctx->cand_cnt[b].need(need_us / 3); }
+            }
             if (big_n && b == 0) {
                 ctx->sort_keys[0].need(need_sc); ctx->sort_keys[1].need(need_sc); ctx->sort_idx[0].need(need_sc); ctx->sort_idx[1].need(need_sc);
                 ctx->seg_off.need(need_us / 3 + 2);
                 if (need_sc >= ((size_t)1 << 31)) return ctx->fail(FY_E_UNSUPPORTED, "score batch too large for the segmented sort");
             }
-            if (use_hi) { ctx->Hh[b].need(need_h); ctx->cand[b].need(need_us / 3 * cap); ctx->cand_score[b].need(need_us / 3 * cap); ctx->cand_cnt[b].need(need_us / 3); }
         }
     }
+    const int h_cycle = std::min(n_hbuf, std::max(1, n_touched_total));
     int hb = 0, sb = 0;
-    bool h_used[2] = {false, false}, s_used[2] = {false, false};
+    bool h_used[3] = {false, false, false}, s_used[2] = {false, false};
     for (int32_t c = 0; c < KC; c++) {
         const int32_t cs = ctx->h_cstart[c], ce = ctx->h_cstart[c + 1];
         int32_t r0 = std::max(cs, ub), r1 = std::min(ce, ue);
@@ -1197,7 +1205,7 @@ static int run_pipeline_impl(fy_rm2_ctx* ctx, bool force_exact) {
             if (ctx->scores[1].cap) sb ^= 1;
         }
         CK(cudaEventRecord(hFree[hb], use_hi ? sT : sS));     // the exact re-score reads H too
-        if (ctx->H[1].cap) hb ^= 1;
+        hb = (hb + 1) % h_cycle;
         ctx->prof.clusters_touched++;
     }
     // join
