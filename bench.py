@@ -319,7 +319,9 @@ def main():
     t_gen = time.time() - t_gen
     workload = {"workload": "RM2 top-%d, %s shape (synthetic, seed %d): %d users x %d items, %d ratings, %d clusters, lambda=%g"
                             % (TOP_N, args.workload, r.seed, r.n_users, r.n_items, r.nnz, r.n_clusters, LAMBDA),
-                "sha256": r.sha256(), "l2": "inputs larger than L2 (per-cluster H is GBs; no flush needed)",
+                "sha256": r.sha256(),
+                "l2": ("inputs larger than L2 (per-cluster H is GBs; no flush needed)" if 12.0 * r.n_items * r.n_items > 4 * 126e6 else
+                       "small test workload: per-cluster H fits in L2, no flush -- not a bench line"),
                 "parallelism": "users sharded over %d GPU(s), ratings replicated" % world}
     if args.impl == "reference":
         return run_reference_arm(args, r, workload)
