@@ -473,6 +473,27 @@ int orc_rm2_run_ext(const orc_params* p,
                 const int32_t* rj = jb->rj;
                 const double pvpi = (n - 1) * log_items - n * log_K;           /* :328-329 */
                 const int64_t q0 = (t - jb->task0) * CH, q1 = q0 + CH < jb->np ? q0 + CH : jb->np;
+                if (p->mode == ORC_MODE_GRAM) {
+                    /* The arithmetic of every (candidate, rated item) pair and the k-ascending accumulation per candidate are
+                     * those of the loop below, with k outermost: G is symmetric (both halves were stored from the same
+                     * value), so row j is read contiguously over the block's candidates instead of one cache line per term. */
+                    double acc[64], pui[64];
+                    for (int64_t q = q0; q < q1; q++) { acc[q - q0] = 0.0; pui[q - q0] = PAT(u, jb->cand_i[q]); }
+                    for (int k = 0; k < n; k++) {
+                        const int64_t j = rj[k];
+                        const double* Gj = G + (size_t)j * (size_t)I;
+                        const double puj = PAT(u, j);
+                        for (int64_t q = q0; q < q1; q++) {
+                            const double sum = Gj[jb->cand_i[q]] - pui[q - q0] * puj;
+                            acc[q - q0] += log(sum);                           /* :348 */
+                        }
+                    }
+                    for (int64_t q = q0; q < q1; q++) {
+                        jb->prefs[q].score = acc[q - q0] + pvpi;                /* :352 */
+                        jb->prefs[q].item = items[jb->cand_i[q]];
+                    }
+                    continue;
+                }
                 for (int64_t q = q0; q < q1; q++) {                             /* :332 */
                     const int64_t i = jb->cand_i[q];
                     double logResult = 0.0;                                    /* :334 */
