@@ -161,6 +161,49 @@ static void gram_block_avx2(const double* P, int64_t K, int64_t I, double* G, in
 #endif
 
 /* ---------------------------------------------------------------------------------------------
+ * LITERAL_FAST only: the neighbour sums of W = 4 G candidates against one rated item at a time.  A is the block's slice
+ * of the cache, interleaved as A[v][q] (q < W); lane q accumulates  sum += P[v][i_q] * P[v][j]  for v = 0..K-1, v != u,
+ * in that order, multiply and add rounded separately -- exactly the scalar loop :342-346 of each (candidate, rated item)
+ * pair, W pairs side by side.  The scalar loop is bound by the latency of its one dependent add chain; W independent
+ * chains fill the pipes.  ORC_LITERAL_SCALAR=1 in the environment forces the scalar loop (the tests compare both).
+ * ------------------------------------------------------------------------------------------- */
+#if defined(__x86_64__)
+#define ORC_DOT_STEP(G)                                                                                  \
+    {                                                                                                    \
+        const __m256d bv = _mm256_set1_pd(b[v]);                                                         \
+        const double* row = A + (size_t)v * (size_t)(4 * (G));                                           \
+        _Pragma("GCC unroll 8")                                                                          \
+        for (int g = 0; g < (G); g++)                                                                    \
+            acc[g] = _mm256_add_pd(acc[g], _mm256_mul_pd(_mm256_loadu_pd(row + 4 * g), bv));             \
+    }
+#define ORC_DOT_KERNEL(G)                                                                                \
+__attribute__((target("avx2")))                                                                          \
+static void dot_block_##G(const double* A, const double* b, int64_t K, int64_t u, double* out) {          \
+    __m256d acc[G];                                                                                      \
+    _Pragma("GCC unroll 8")                                                                              \
+    for (int g = 0; g < (G); g++) acc[g] = _mm256_setzero_pd();                                          \
+    for (int64_t v = 0; v < u; v++) ORC_DOT_STEP(G)                                                      \
+    for (int64_t v = u + 1; v < K; v++) ORC_DOT_STEP(G)                                                  \
+    _Pragma("GCC unroll 8")                                                                              \
+    for (int g = 0; g < (G); g++) _mm256_storeu_pd(out + 4 * g, acc[g]);                                 \
+}
+ORC_DOT_KERNEL(1) ORC_DOT_KERNEL(2) ORC_DOT_KERNEL(3) ORC_DOT_KERNEL(4)
+ORC_DOT_KERNEL(5) ORC_DOT_KERNEL(6) ORC_DOT_KERNEL(7) ORC_DOT_KERNEL(8)
+static void dot_block(int G, const double* A, const double* b, int64_t K, int64_t u, double* out) {
+    switch (G) {
+        case 1: dot_block_1(A, b, K, u, out); break;
+        case 2: dot_block_2(A, b, K, u, out); break;
+        case 3: dot_block_3(A, b, K, u, out); break;
+        case 4: dot_block_4(A, b, K, u, out); break;
+        case 5: dot_block_5(A, b, K, u, out); break;
+        case 6: dot_block_6(A, b, K, u, out); break;
+        case 7: dot_block_7(A, b, K, u, out); break;
+        default: dot_block_8(A, b, K, u, out); break;
+    }
+}
+#endif
+
+/* ---------------------------------------------------------------------------------------------
  * Statistics: jobs RM2-1 (userSum + truncated total) and RM2-2 (p(i|C)).
  * ------------------------------------------------------------------------------------------- */
 int orc_rm2_stats(const int32_t* r_user, const int32_t* r_item, const float* r_score, int64_t nnz,
@@ -465,7 +508,18 @@ int orc_rm2_run_ext(const orc_params* p,
                 if (slot[u] >= 0) for (int64_t t = job[u].task0, e = job[u].task0 + (job[u].np + CH - 1) / CH; t < e; t++) task_user[t] = u;
         }
         if (!oom) {
-#pragma omp parallel for schedule(dynamic, 1)
+            /* candidates per interleaved block: the block (K x W doubles) should stay in a core's L2 */
+            int block_w = 0;
+#if defined(__x86_64__)
+            if (p->mode == ORC_MODE_LITERAL_FAST && __builtin_cpu_supports("avx2") && !getenv("ORC_LITERAL_SCALAR")) {
+                int64_t w = ((int64_t)768 * 1024 / (8 * K)) & ~(int64_t)3;
+                block_w = (int)(w < 4 ? 4 : (w > 32 ? 32 : w));
+            }
+#endif
+#pragma omp parallel
+            {
+            double* blockA = block_w ? (double*)malloc(sizeof(double) * (size_t)K * (size_t)block_w) : NULL;
+#pragma omp for schedule(dynamic, 1)
             for (int64_t t = 0; t < n_tasks; t++) {
                 const int64_t u = task_user[t];
                 const ujob_t* jb = &job[u];
@@ -473,6 +527,29 @@ int orc_rm2_run_ext(const orc_params* p,
                 const int32_t* rj = jb->rj;
                 const double pvpi = (n - 1) * log_items - n * log_K;           /* :328-329 */
                 const int64_t q0 = (t - jb->task0) * CH, q1 = q0 + CH < jb->np ? q0 + CH : jb->np;
+#if defined(__x86_64__)
+                if (blockA) {
+                    double acc[64], sums[32];
+                    for (int64_t q = q0; q < q1; q++) acc[q - q0] = 0.0;
+                    for (int64_t qb = q0; qb < q1; qb += block_w) {
+                        const int nq = (int)(q1 - qb < block_w ? q1 - qb : block_w);
+                        const int Gn = (nq + 3) / 4, W = 4 * Gn;
+                        for (int q = 0; q < W; q++) {                           /* pad lanes repeat the last candidate */
+                            const double* a = P + (size_t)jb->cand_i[qb + (q < nq ? q : nq - 1)] * (size_t)K;
+                            for (int64_t v = 0; v < K; v++) blockA[(size_t)v * (size_t)W + (size_t)q] = a[v];
+                        }
+                        for (int k = 0; k < n; k++) {                           /* :337 */
+                            dot_block(Gn, blockA, P + (size_t)rj[k] * (size_t)K, K, u, sums);   /* :339-346 */
+                            for (int q = 0; q < nq; q++) acc[qb - q0 + q] += log(sums[q]);       /* :348 */
+                        }
+                    }
+                    for (int64_t q = q0; q < q1; q++) {
+                        jb->prefs[q].score = acc[q - q0] + pvpi;                /* :352 */
+                        jb->prefs[q].item = items[jb->cand_i[q]];
+                    }
+                    continue;
+                }
+#endif
                 if (p->mode == ORC_MODE_GRAM) {
                     /* The arithmetic of every (candidate, rated item) pair and the k-ascending accumulation per candidate are
                      * those of the loop below, with k outermost: G is symmetric (both halves were stored from the same
@@ -519,6 +596,8 @@ int orc_rm2_run_ext(const orc_params* p,
                     jb->prefs[q].score = logResult;
                     jb->prefs[q].item = items[i];
                 }
+            }
+            free(blockA);
             }
 #pragma omp parallel for schedule(dynamic, 1)
             for (int64_t u = 0; u < K; u++) {

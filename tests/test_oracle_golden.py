@@ -37,6 +37,23 @@ def test_literal_fast_is_bit_identical_and_gram_agrees(golden, golden_ratings):
     assert np.max(np.abs(a["score64"] - c["score64"]) / np.abs(a["score64"])) < 1e-13
 
 
+def test_blocked_literal_fast_equals_the_scalar_loop(monkeypatch):
+    # LITERAL_FAST scores 4 G candidates side by side (AVX2 lanes, one sequential sum per lane); ORC_LITERAL_SCALAR=1
+    # forces the one-pair-at-a-time loop.  Same bits, for every lambda (lambda = 0 reaches log 0 = -inf), ragged blocks
+    # (candidate counts that are not multiples of 4) and the strided timing mode; and both equal the row-major literal loop.
+    r = datagen.generate("small")
+    for lam, top_n, kw in ((0.1, 100, {}), (0.0, 7, {}), (1.0, 100, {}), (0.5, 100, {"cand_stride": 7})):
+        monkeypatch.delenv("ORC_LITERAL_SCALAR", raising=False)
+        a = _run(r, lam, r.n_items, top_n, mode=orc.MODE_LITERAL_FAST, threads=3, **kw)
+        monkeypatch.setenv("ORC_LITERAL_SCALAR", "1")
+        b = _run(r, lam, r.n_items, top_n, mode=orc.MODE_LITERAL_FAST, threads=3, **kw)
+        monkeypatch.delenv("ORC_LITERAL_SCALAR", raising=False)
+        assert np.array_equal(a["item"], b["item"]) and a["score64"].tobytes() == b["score64"].tobytes(), (lam, kw)
+        if not kw:
+            c = _run(r, lam, r.n_items, top_n, mode=orc.MODE_LITERAL, threads=1)
+            assert np.array_equal(a["item"], c["item"]) and a["score64"].tobytes() == c["score64"].tobytes(), lam
+
+
 def test_statistics_match_golden(golden, golden_ratings):
     # T/rm/TestHDFSRM2.java:70-71: userSum and itemColl; RMTestData.java:426 totalSum
     r = golden_ratings
