@@ -51,7 +51,9 @@ class RM2Job:
     """conf: dict with the reference's keys (numberOfItems and numberOfClusters are required,
     RMRecommenderDriver.java:91-92)."""
 
-    def __init__(self, conf, device=0, shard_rank=0, shard_count=1):
+    def __init__(self, conf, device=0, shard_rank=0, shard_count=1, n_gpus=None):
+        # n_gpus (or conf["rm2.gpu.count"], the key integration/java/.../RM2GpuJob.java reads): one context over that many
+        # devices from `device` on -- the reduce-task fan-out of RM2Job.java:251 inside one native call
         for k in ("numberOfItems", "numberOfClusters"):
             if k not in conf:
                 raise KeyError("missing required option --%s" % k)
@@ -64,7 +66,8 @@ class RM2Job:
                               number_of_items=int(self.conf["numberOfItems"]),
                               top_n=int(self.conf["numberOfRecommendations"]),
                               filter_users=int(self.conf["filterUsers"]),
-                              device=device, shard_rank=shard_rank, shard_count=shard_count)
+                              device=device, shard_rank=shard_rank, shard_count=shard_count,
+                              n_gpus=int(n_gpus if n_gpus is not None else self.conf.get("rm2.gpu.count", 0)))
 
     def close(self):
         self._eng.close()
