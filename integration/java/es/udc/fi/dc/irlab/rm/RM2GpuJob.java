@@ -33,8 +33,9 @@ import es.udc.fi.dc.irlab.util.HadoopUtils;
  * Differences from RM2Job, all deliberate:
  * <ul>
  * <li>Cassandra on either side (useCassandraInput / useCassandraOutput, both <code>true</code> by default inside
- * RM2Job) is not read or written natively: those runs are delegated to <code>super.run</code> with the fine-seam
- * reducers ({@link RM2GpuCassandraReducer}) when <code>rm2.gpu.fine=true</code>, and otherwise to the stock job.</li>
+ * RM2Job) is not read or written natively: those runs are delegated to <code>super.run</code>, the stock job; the GPU
+ * option there is the fine seam, {@link RM2GpuCassandraReducer} selected by a one-line change in
+ * RM2Job.runItemRecommendation (INTEGRATION.md, section 3).</li>
  * <li><code>rm2.gpu.count</code> (default 1) devices starting at <code>rm2.gpu.device</code> (default 0) score the users
  * in one native call (fy_rm2_params.n_gpus); the reduce-task fan-out of RM2-3 (numReduceTasks = numberOfClusters)
  * has no other counterpart here.</li>
@@ -87,6 +88,7 @@ public class RM2GpuJob extends RM2Job {
             while (reader.next(key, val)) {
                 nnz++;
             }
+            reader.close();
         }
         final IntBuffer user = ints(nnz), item = ints(nnz);
         final FloatBuffer score = floats(nnz);
@@ -98,6 +100,7 @@ public class RM2GpuJob extends RM2Job {
                 item.put(key.getSecond());
                 score.put(val.get());
             }
+            reader.close();
         }
 
         /* 2. clustering / clusteringCount: the two DistributedCache files of RM2-3 */
@@ -110,6 +113,7 @@ public class RM2GpuJob extends RM2Job {
             while (reader.next(k, v)) {
                 nUsers++;
             }
+            reader.close();
         }
         final IntBuffer clUser = ints(nUsers), clCluster = ints(nUsers), clusterSize = ints(numberOfClusters);
         for (final SequenceFile.Reader reader : HadoopUtils.getSequenceReaders(clustering, conf)) {
@@ -118,12 +122,14 @@ public class RM2GpuJob extends RM2Job {
                 clUser.put(k.get());
                 clCluster.put(v.get());
             }
+            reader.close();
         }
         for (final SequenceFile.Reader reader : HadoopUtils.getSequenceReaders(clusteringCount, conf)) {
             final IntWritable k = new IntWritable(), v = new IntWritable();
             while (reader.next(k, v)) {
                 clusterSize.put(k.get(), v.get());
             }
+            reader.close();
         }
 
         /* 3. the whole of RM2-1..3 on rm2.gpu.count devices */
@@ -155,7 +161,12 @@ public class RM2GpuJob extends RM2Job {
                 for (int k = 0; k < nUsers; k++) {
                     order[k] = k;
                 }
-                java.util.Arrays.sort(order, (a, b) -> Integer.compare(clUser.get(a), clUser.get(b)));
+                java.util.Arrays.sort(order, new java.util.Comparator<Integer>() { // the pom compiles with -source 1.7: no lambdas
+                    @Override
+                    public int compare(final Integer a, final Integer b) {
+                        return Integer.compare(clUser.get(a), clUser.get(b));
+                    }
+                });
                 for (final int k : order) {
                     sums.append(new IntWritable(clUser.get(k)), new DoubleWritable(userSum.get(k)));
                 }

@@ -80,6 +80,9 @@ def test_java_source_is_well_formed(path):
                 assert stack and stack.pop() == pairs[ch], "unbalanced %r" % ch
     assert not stack, "unclosed %r" % stack
     code = "".join(v for t, v in toks if t not in Token.Comment)
+    # the reference's pom.xml compiles with <source>1.7</source>: no lambdas, no method references
+    bare = "".join(v for t, v in toks if t not in Token.Comment and t not in Token.Literal.String)
+    assert "->" not in bare and "::" not in bare, "Java 8 syntax in a -source 1.7 build"
     pkg = re.search(r"^\s*package\s+([\w.]+)\s*;", code, re.M)
     assert pkg, "no package declaration"
     rel = os.path.relpath(os.path.dirname(path), JAVA_ROOT).replace(os.sep, ".")
